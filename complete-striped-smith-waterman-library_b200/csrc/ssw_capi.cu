@@ -1,0 +1,195 @@
+/*
+ * ssw_capi.cu -- the ssw.h entry points (drop-in boundary) on top of the batch engine.
+ *
+ *   ssw_init / init_destroy      <- src/ssw.c:826-853
+ *   ssw_align                    <- src/ssw.c:855-977   (a batch of one pair)
+ *   align_destroy                <- src/ssw.c:979-982
+ *   mark_mismatch, add_cigar, store_previous_m <- src/ssw.c:984-1074 (host-side CIGAR post-processing)
+ *   encoded_ops                  <- src/ssw.c:127-160
+ *   ssw_align_batch              new: many pairs per call (include/ssw_batch.h)
+ */
+#include <mutex>
+#include <vector>
+#include <string.h>
+
+#include "ssw_common.cuh"
+#include "../../include/ssw.h"
+#include "../../include/ssw_batch.h"
+
+/* ASCII CIGAR letter -> BAM op code; letters not in "MIDNSHP=X" map to 0 like the reference table */
+extern "C" const uint8_t encoded_ops[128] = {
+	0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+	0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, /* '=' */ 7, 0, 0,
+	0, 0, 0, 0, /* D */ 2, 0, 0, 0, /* H */ 5, /* I */ 1, 0, 0, 0, /* M */ 0, /* N */ 3, 0,
+	/* P */ 6, 0, 0, /* S */ 4, 0, 0, 0, 0, /* X */ 8, 0, 0, 0, 0, 0, 0, 0,
+	0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+};
+
+/* The profile of the reference holds striped SSE2 tables (ssw.c:115-123); ours only
+ * records what the engine needs.  read and mat are borrowed, as in the reference. */
+struct _profile {
+	const int8_t* read;
+	const int8_t* mat;
+	int32_t readLen;
+	int32_t n;
+	int8_t score_size;
+};
+
+namespace {
+std::mutex g_mu;
+ssw_engine* g_engine = nullptr;
+
+ssw_engine* default_engine()
+{
+	if (!g_engine) g_engine = ssw_engine_create(-1);
+	return g_engine;
+}
+
+s_align* record_from(const ssw_batch_result& r, const uint32_t* pool)
+{
+	if (r.status) return nullptr;
+	s_align* a = (s_align*)calloc(1, sizeof(s_align));
+	a->score1 = r.score1; a->score2 = r.score2;
+	a->ref_begin1 = r.ref_begin1; a->ref_end1 = r.ref_end1;
+	a->read_begin1 = r.read_begin1; a->read_end1 = r.read_end1;
+	a->ref_end2 = r.ref_end2; a->flag = r.flag;
+	if (r.cigar_off >= 0 && r.cigar_len > 0) {
+		a->cigar = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)r.cigar_len);   /* libc heap: callers free() it */
+		memcpy(a->cigar, pool + r.cigar_off, sizeof(uint32_t) * (size_t)r.cigar_len);
+		a->cigarLen = r.cigar_len;
+	}
+	return a;
+}
+}  // namespace
+
+extern "C" s_profile* ssw_init(const int8_t* read, const int32_t readLen, const int8_t* mat, const int32_t n, const int8_t score_size)
+{
+	s_profile* p = (s_profile*)calloc(1, sizeof(struct _profile));
+	p->read = read; p->mat = mat; p->readLen = readLen; p->n = n; p->score_size = score_size;
+	return p;
+}
+
+extern "C" void init_destroy(s_profile* p) { free(p); }
+
+extern "C" void align_destroy(s_align* a)
+{
+	if (!a) return;
+	free(a->cigar);
+	free(a);
+}
+
+extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t refLen,
+                              const uint8_t weight_gapO, const uint8_t weight_gapE, const uint8_t flag,
+                              const uint16_t filters, const int32_t filterd, const int32_t maskLen)
+{
+	if (!prof) return NULL;
+	if (maskLen < 15)   /* ssw.c:876-878: printed on every call */
+		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+	std::lock_guard<std::mutex> lock(g_mu);
+	ssw_engine* e = default_engine();
+	if (!e) return NULL;
+	const int64_t qoff[2] = {0, prof->readLen}, roff[2] = {0, refLen};
+	if (ssw_engine_set_sequences(e, 1, prof->read, qoff, 1, ref, roff)) return NULL;
+	ssw_batch_params P;
+	memset(&P, 0, sizeof(P));
+	P.mat = prof->mat; P.n = prof->n; P.gap_open = weight_gapO; P.gap_extend = weight_gapE;
+	P.flag = flag; P.filters = filters; P.filterd = filterd; P.mask_len = maskLen < 0 ? 0 : maskLen; P.score_size = prof->score_size;
+	ssw_batch_result r;
+	std::vector<uint32_t> pool((size_t)prof->readLen + (size_t)refLen + 8);
+	int64_t used = 0;
+	const int32_t pq = 0, pr = 0;
+	if (ssw_engine_align(e, &P, 1, &pq, &pr, &r, pool.data(), (int64_t)pool.size(), &used)) return NULL;
+	return record_from(r, pool.data());
+}
+
+extern "C" int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
+                               int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                               int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
+                               int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                               s_align** out)
+{
+	if (!e || !params || !out) return -1;
+	if (params->mask_len >= 0 && params->mask_len < 15)
+		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+	int rc = ssw_engine_set_sequences(e, n_queries, queries, query_off, n_refs, refs, ref_off);
+	if (rc) return rc;
+	std::vector<ssw_batch_result> res((size_t)n_pairs);
+	/* CIGAR pool: a path has at most readLen + refLen + 2 words */
+	int64_t cap = 0;
+	if (params->flag & 7) {
+		for (int64_t p = 0; p < n_pairs; ++p) {
+			const int32_t q = pair_query ? pair_query[p] : (int32_t)(p / n_refs), r = pair_ref ? pair_ref[p] : (int32_t)(p % n_refs);
+			if (q < 0 || q >= n_queries || r < 0 || r >= n_refs) return -1;
+			const int64_t ql = query_off[q + 1] - query_off[q], rl = ref_off[r + 1] - ref_off[r];
+			/* a path has <= (query span + reference span + 2) words; a positive-scoring path cannot
+			 * delete more than (query length * max score / gap_extend) reference bases */
+			int64_t span = rl;
+			if (params->gap_extend > 0) { const int64_t b = ql + ql * 127 / params->gap_extend; if (b < span) span = b; }
+			cap += ql + span + 4;
+		}
+	}
+	std::vector<uint32_t> pool((size_t)cap + 8);
+	int64_t used = 0;
+	rc = ssw_engine_align(e, params, n_pairs, pair_query, pair_ref, res.data(), pool.data(), (int64_t)pool.size(), &used);
+	if (rc) return rc;
+	for (int64_t p = 0; p < n_pairs; ++p) out[p] = record_from(res[p], pool.data());
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* CIGAR post-processing (host, O(alignment length)); exported with the reference's names        */
+/* ------------------------------------------------------------------------------------------- */
+
+/* append (length, op) to a growable CIGAR; *p = used, *s = capacity (ssw.c:984-992) */
+extern "C" uint32_t* add_cigar(uint32_t* new_cigar, int32_t* p, int32_t* s, uint32_t length, char op)
+{
+	if (*p >= *s) {
+		int32_t cap = *s < 4 ? 4 : *s;
+		while (cap <= *p) cap *= 2;
+		*s = cap;
+		new_cigar = (uint32_t*)realloc(new_cigar, sizeof(uint32_t) * (size_t)cap);
+	}
+	new_cigar[(*p)++] = to_cigar_int(length, (unsigned char)op);
+	return new_cigar;
+}
+
+/* flush a pending '=' or 'X' run; choice 0: current op is not M, 1: current base matches, 2: mismatches (ssw.c:994-1009) */
+extern "C" uint32_t* store_previous_m(int8_t choice, uint32_t* length_m, uint32_t* length_x, int32_t* p, int32_t* s, uint32_t* new_cigar)
+{
+	if (*length_m && choice != 1) { new_cigar = add_cigar(new_cigar, p, s, *length_m, '='); *length_m = 0; }
+	else if (*length_x && choice != 2) { new_cigar = add_cigar(new_cigar, p, s, *length_x, 'X'); *length_x = 0; }
+	return new_cigar;
+}
+
+extern "C" int32_t mark_mismatch(int32_t ref_begin1, int32_t read_begin1, int32_t read_end1,
+                                 const int8_t* ref, const int8_t* read, int32_t readLen,
+                                 uint32_t** cigar, int32_t* cigarLen)
+{
+	int32_t used = 0, cap = *cigarLen + 2, nm = 0;
+	uint32_t* out = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(cap > 0 ? cap : 1));
+	uint32_t run_eq = 0, run_x = 0;
+	const int8_t* rp = ref + ref_begin1;
+	const int8_t* qp = read + read_begin1;
+	if (read_begin1 > 0) out = add_cigar(out, &used, &cap, (uint32_t)read_begin1, 'S');
+	for (int32_t i = 0; i < *cigarLen; ++i) {
+		const char op = cigar_int_to_op((*cigar)[i]);
+		const int32_t len = (int32_t)cigar_int_to_len((*cigar)[i]);
+		if (op == 'M') {
+			for (int32_t k = 0; k < len; ++k, ++rp, ++qp) {
+				if (*rp != *qp) { ++nm; out = store_previous_m(2, &run_eq, &run_x, &used, &cap, out); ++run_x; }
+				else { out = store_previous_m(1, &run_eq, &run_x, &used, &cap, out); ++run_eq; }
+			}
+		} else if (op == 'I' || op == 'D') {
+			if (op == 'I') qp += len; else rp += len;
+			nm += len;
+			out = store_previous_m(0, &run_eq, &run_x, &used, &cap, out);
+			out = add_cigar(out, &used, &cap, (uint32_t)len, op);
+		}
+	}
+	out = store_previous_m(0, &run_eq, &run_x, &used, &cap, out);
+	if (readLen - read_end1 - 1 > 0) out = add_cigar(out, &used, &cap, (uint32_t)(readLen - read_end1 - 1), 'S');
+	*cigarLen = used;
+	free(*cigar);
+	*cigar = out;
+	return nm;
+}

@@ -1,0 +1,578 @@
+/*
+ * ssw_engine.cu -- host side of the batched aligner: planning, device buffers,
+ * kernel launches and result assembly.  It is the batched equivalent of the
+ * reference's ssw_align orchestrator (src/ssw.c:855-977):
+ *
+ *   P1  forward fill, byte semantics first when a byte profile exists, re-run
+ *       with word semantics on overflow            (ssw.c:881-899)
+ *   --  score <= 0 / flag gating                    (ssw.c:900-916)
+ *   P2  reverse fill on the reversed query prefix with early termination
+ *                                                   (ssw.c:919-936)
+ *   P3  banded traceback + CIGAR re-scoring + retry (ssw.c:938-973)
+ *
+ * Nothing here computes alignments on the CPU; all DP work is in the kernels.
+ */
+#include <algorithm>
+#include <vector>
+#include <string>
+#include <string.h>
+
+#include "ssw_common.cuh"
+#include "ssw_host.h"
+#include "ssw_fill.cuh"
+#include "ssw_resolve.cuh"
+#include "ssw_traceback.cuh"
+#include "../../include/ssw_batch.h"
+
+namespace {
+
+/* kernel instance = (lanes per group, rows per lane); rows covered = G*R */
+struct Inst { int G, R; };
+static const Inst kInst[] = {
+	{8, 4}, {8, 5}, {8, 8}, {8, 10}, {16, 8}, {16, 10}, {32, 8}, {32, 10}, {32, 16},
+};
+static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
+static const int kMaxRows = 512;
+
+static int pick_inst(int lp)
+{
+	for (int i = 0; i < kNumInst; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
+	return -1;
+}
+/* reverse pass: one alignment per warp */
+static int pick_inst_g32(int lp)
+{
+	for (int i = 0; i < kNumInst; ++i) if (kInst[i].G == 32 && kInst[i].G * kInst[i].R >= lp) return i;
+	return -1;
+}
+
+}  // namespace
+
+struct ssw_engine {
+	int device = 0;
+	std::string dev_name;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+
+	/* resident sequences */
+	int32_t n_q = 0, n_r = 0;
+	std::vector<int64_t> q_off;      /* n_q + 1 */
+	std::vector<int64_t> r_off;      /* offset of column 0 inside the padded device array */
+	std::vector<int32_t> r_len;
+	std::vector<int8_t> h_q, h_r;    /* host copies (codes), used to re-pad when the alphabet size changes */
+	std::vector<int64_t> h_r_off;
+	int padded_n = -1;               /* null letter currently stored in the reference pads */
+	SswDevBuf d_q, d_r, d_mat;
+
+	/* scratch */
+	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb;
+	int64_t opt_chunk = 0;
+	ssw_engine_timing timing;
+	SswTimer t_total, t_k;
+
+	int upload_refs(int n);
+	int run_fill(const std::vector<SswItem>& items, int inst, int dir, bool write_cm, bool term,
+	             const ssw_batch_params& P, float* ms_acc);
+};
+
+/* ------------------------------------------------------------------------------------------- */
+/* fill kernel dispatch                                                                          */
+/* ------------------------------------------------------------------------------------------- */
+
+template <int G, int R>
+static int launch_fill(ssw_engine* e, int n_items, int dir, bool write_cm, bool term, const ssw_batch_params& P)
+{
+	constexpr int GPW = 32 / G;
+	const int per_cta = SSW_FILL_WARPS * GPW;
+	const int grid = (n_items + per_cta - 1) / per_cta;
+	const size_t smem = ssw_fill_smem_bytes<R>(P.n);
+	const SswItem* items = e->d_items.as<SswItem>();
+	const int8_t* q = e->d_q.as<int8_t>();
+	const int8_t* r = e->d_r.as<int8_t>();
+	const int8_t* mat = e->d_mat.as<int8_t>();
+	uint32_t* cm = e->d_colmax.as<uint32_t>();
+	SswItemBest* bests = e->d_bests.as<SswItemBest>();
+#define SSW_FILL_GO(DIR, CM, TERM)                                                                               \
+	do {                                                                                                         \
+		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM>;                                                        \
+		if (smem > 48 * 1024)                                                                                    \
+			SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+		ssw_launch(kern, dim3(grid), dim3(SSW_FILL_THREADS), smem, e->stream, items, n_items, q, r, mat, (int)P.n, \
+		           (int)P.gap_open, (int)P.gap_extend, cm, bests);                                               \
+	} while (0)
+	(void)write_cm; (void)term;
+	if (dir > 0) SSW_FILL_GO(1, true, false);          /* forward: column maxima always recorded */
+	else SSW_FILL_GO(-1, false, G == 32);               /* reverse: one alignment per warp, early termination */
+#undef SSW_FILL_GO
+	SSW_CUDA_OK(cudaGetLastError());
+	return 0;
+}
+
+int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, bool write_cm, bool term,
+                         const ssw_batch_params& P, float* ms_acc)
+{
+	const int n_items = (int)items.size();
+	if (n_items == 0) return 0;
+	if (d_items.ensure(sizeof(SswItem) * items.size())) return -1;
+	if (d_bests.ensure(sizeof(SswItemBest) * items.size())) return -1;
+	SSW_CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), sizeof(SswItem) * items.size(), cudaMemcpyHostToDevice, stream));
+	t_k.start(stream);
+	int rc = -1;
+	switch (inst) {
+	case 0: rc = launch_fill<8, 4>(this, n_items, dir, write_cm, term, P); break;
+	case 1: rc = launch_fill<8, 5>(this, n_items, dir, write_cm, term, P); break;
+	case 2: rc = launch_fill<8, 8>(this, n_items, dir, write_cm, term, P); break;
+	case 3: rc = launch_fill<8, 10>(this, n_items, dir, write_cm, term, P); break;
+	case 4: rc = launch_fill<16, 8>(this, n_items, dir, write_cm, term, P); break;
+	case 5: rc = launch_fill<16, 10>(this, n_items, dir, write_cm, term, P); break;
+	case 6: rc = launch_fill<32, 8>(this, n_items, dir, write_cm, term, P); break;
+	case 7: rc = launch_fill<32, 10>(this, n_items, dir, write_cm, term, P); break;
+	case 8: rc = launch_fill<32, 16>(this, n_items, dir, write_cm, term, P); break;
+	default: break;
+	}
+	*ms_acc += t_k.stop(stream);
+	return rc;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* engine life cycle                                                                              */
+/* ------------------------------------------------------------------------------------------- */
+
+extern "C" ssw_engine* ssw_engine_create(int device)
+{
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+		fprintf(stderr, "[libssw-b200] no usable CUDA device: this library has no CPU compute path\n");
+		return nullptr;
+	}
+	if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+	if (device >= count || cudaSetDevice(device) != cudaSuccess) {
+		fprintf(stderr, "[libssw-b200] cannot select CUDA device %d (of %d)\n", device, count);
+		return nullptr;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return nullptr;
+	ssw_engine* e = new ssw_engine();
+	e->device = device;
+	e->dev_name = prop.name;
+	e->sm_count = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
+	memset(&e->timing, 0, sizeof(e->timing));
+	return e;
+}
+
+extern "C" void ssw_engine_destroy(ssw_engine* e)
+{
+	if (!e) return;
+	cudaSetDevice(e->device);
+	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb};
+	for (SswDevBuf* b : bufs) b->release();
+	if (e->stream) cudaStreamDestroy(e->stream);
+	delete e;
+}
+
+extern "C" const char* ssw_engine_device_name(const ssw_engine* e) { return e ? e->dev_name.c_str() : ""; }
+
+extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value)
+{
+	if (!e || !name) return -1;
+	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
+	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
+	return -1;
+}
+
+extern "C" int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t)
+{
+	if (!e || !t) return -1;
+	*t = e->timing;
+	return 0;
+}
+
+/* references are stored as  [PAD x null] codes [PAD x null]  with null = n (scores as a dead letter) */
+int ssw_engine::upload_refs(int n)
+{
+	if (padded_n == n && d_r.p) return 0;
+	int64_t total = 0;
+	r_off.resize(n_r);
+	for (int i = 0; i < n_r; ++i) {
+		total += SSW_REF_PAD;
+		r_off[i] = total;
+		total += r_len[i];
+		total += SSW_REF_PAD;
+		total = (total + 15) / 16 * 16;
+	}
+	total += 2 * SSW_REF_PAD;
+	std::vector<int8_t> padded((size_t)total, (int8_t)n);
+	for (int i = 0; i < n_r; ++i) memcpy(padded.data() + r_off[i], h_r.data() + h_r_off[i], (size_t)r_len[i]);
+	if (d_r.ensure((size_t)total)) return -1;
+	SSW_CUDA_OK(cudaMemcpyAsync(d_r.p, padded.data(), (size_t)total, cudaMemcpyHostToDevice, stream));
+	SSW_CUDA_OK(cudaStreamSynchronize(stream));
+	padded_n = n;
+	return 0;
+}
+
+extern "C" int ssw_engine_set_sequences(ssw_engine* e,
+                                        int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                                        int32_t n_refs, const int8_t* refs, const int64_t* ref_off)
+{
+	if (!e || n_queries < 0 || n_refs < 0 || (n_queries && (!queries || !query_off)) || (n_refs && (!refs || !ref_off))) return -1;
+	SSW_CUDA_OK(cudaSetDevice(e->device));
+	e->n_q = n_queries; e->n_r = n_refs;
+	e->q_off.assign(query_off, query_off + n_queries + 1);
+	e->h_q.assign(queries, queries + query_off[n_queries]);
+	e->h_r_off.assign(ref_off, ref_off + n_refs + 1);
+	e->h_r.assign(refs, refs + ref_off[n_refs]);
+	e->r_len.resize(n_refs);
+	for (int i = 0; i < n_refs; ++i) e->r_len[i] = (int32_t)(ref_off[i + 1] - ref_off[i]);
+	if (e->d_q.ensure(e->h_q.size() + 16)) return -1;
+	SSW_CUDA_OK(cudaMemcpyAsync(e->d_q.p, e->h_q.data(), e->h_q.size(), cudaMemcpyHostToDevice, e->stream));
+	e->padded_n = -1;           /* the null letter depends on the alphabet size given at align time */
+	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* the batched ssw_align                                                                          */
+/* ------------------------------------------------------------------------------------------- */
+
+namespace {
+
+struct Aln {            /* one requested pair while it moves through the phases */
+	int32_t q, r;
+	int32_t read_len, ref_len, mask_len;
+	int32_t word;       /* semantics of the accepted forward result */
+	SswFillResult fwd;
+	int32_t rev_score, rev_pos, rev_row;
+};
+
+static inline int lp_of(int len, int word) { int g = word ? 8 : 16; return (len + g - 1) / g * g; }
+
+}  // namespace
+
+/* Plan and run one forward fill + resolve over the alignments `sel` (indices into alns) with the given semantics. */
+static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>& alns, const std::vector<int64_t>& sel,
+                        int word, int bias, int max_mat)
+{
+	if (sel.empty()) return 0;
+	/* order: kernel instance, reference, then query length so that partners are alike */
+	struct Key { int inst; int32_t r; int32_t lp; int64_t idx; };
+	std::vector<Key> keys(sel.size());
+	for (size_t i = 0; i < sel.size(); ++i) {
+		const Aln& a = alns[sel[i]];
+		const int lp = lp_of(a.read_len, word);
+		const int inst = pick_inst(lp);
+		if (inst < 0) {
+			fprintf(stderr, "[libssw-b200] query of %d residues exceeds the single-strip limit of %d rows\n", a.read_len, kMaxRows);
+			return -2;
+		}
+		keys[i] = Key{inst, a.r, lp, sel[i]};
+	}
+	std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
+		if (x.inst != y.inst) return x.inst < y.inst;
+		if (x.r != y.r) return x.r < y.r;
+		if (x.lp != y.lp) return x.lp < y.lp;
+		return x.idx < y.idx;
+	});
+
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	const size_t cm_budget_words = std::max<size_t>((size_t)1 << 22, (free_b + e->d_colmax.cap) / 2 / 4);
+
+	size_t k = 0;
+	while (k < keys.size()) {
+		/* one launch = one kernel instance, bounded by the column-maximum budget */
+		const int inst = keys[k].inst;
+		std::vector<SswItem> items;
+		std::vector<SswAlnDesc> descs;
+		std::vector<int64_t> desc_aln;
+		size_t cm_words = 0;
+		int64_t cells = 0;
+		/* pass 1: form pair-tasks, decide the chunk length from the amount of work in this launch */
+		struct PT { int64_t a, b; int32_t r; };
+		std::vector<PT> pts;
+		size_t k_end = k;
+		int64_t total_cols = 0;
+		while (k_end < keys.size() && keys[k_end].inst == inst) {
+			const int32_t r = keys[k_end].r;
+			const size_t words = ((size_t)e->r_len[r] + 3) / 4 * 4;
+			if (!pts.empty() && cm_words + words > cm_budget_words) break;
+			PT pt; pt.a = keys[k_end].idx; pt.b = -1; pt.r = r;
+			++k_end;
+			if (k_end < keys.size() && keys[k_end].inst == inst && keys[k_end].r == r) { pt.b = keys[k_end].idx; ++k_end; }
+			pts.push_back(pt);
+			cm_words += words;
+			total_cols += e->r_len[r];
+		}
+		const int64_t target_items = (int64_t)e->sm_count * 32 * 8;
+		int64_t auto_chunk = (total_cols / target_items + 3) / 4 * 4;
+
+		cm_words = 0;
+		for (const PT& pt : pts) {
+			const Aln& A = alns[pt.a];
+			const Aln* B = pt.b >= 0 ? &alns[pt.b] : nullptr;
+			const int32_t ref_len = e->r_len[pt.r];
+			const int lpa = lp_of(A.read_len, word), lpb = B ? lp_of(B->read_len, word) : 0;
+			const int max_lp = std::max(lpa, lpb), max_len = std::max(A.read_len, B ? B->read_len : 0);
+			/* a path with positive score spans at most max_lp diagonal steps plus (total positive score)/gapE gap columns */
+			int64_t warm = 0, chunk = ref_len;
+			if (P.gap_extend > 0 && max_mat > 0) {
+				warm = (int64_t)max_lp + ((int64_t)max_len * max_mat + P.gap_extend - 1) / P.gap_extend + 4;
+				warm = (warm + 3) / 4 * 4;
+				chunk = e->opt_chunk > 0 ? e->opt_chunk : std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
+			}
+			if (chunk >= ref_len) chunk = std::max<int32_t>(ref_len, 4);
+			chunk = (chunk + 3) / 4 * 4;
+			const int n_chunks = std::max<int>(1, (int)((ref_len + chunk - 1) / chunk));
+			const int first_item = (int)items.size();
+			for (int c = 0; c < n_chunks; ++c) {
+				SswItem it;
+				memset(&it, 0, sizeof(it));
+				it.qa.off = (int32_t)e->q_off[A.q]; it.qa.len = A.read_len; it.qa.lp = lpa; it.qa.rev = 0;
+				if (B) { it.qb.off = (int32_t)e->q_off[B->q]; it.qb.len = B->read_len; it.qb.lp = lpb; it.qb.rev = 0; }
+				it.ref_off = e->r_off[pt.r]; it.ref_len = ref_len; it.cend = 0;
+				it.p0 = (int32_t)(c * chunk);
+				it.p1 = (int32_t)std::min<int64_t>(ref_len, (c + 1) * chunk);
+				it.warm = (int32_t)std::min<int64_t>(warm, it.p0);
+				it.term_a = -1;
+				it.cm_off = (int64_t)cm_words;
+				items.push_back(it);
+				cells += (int64_t)(it.p1 - it.p0 + it.warm) * kInst[inst].G * kInst[inst].R * 2;
+			}
+			for (int h = 0; h < (B ? 2 : 1); ++h) {
+				const Aln& X = h ? *B : A;
+				SswAlnDesc d;
+				d.first_item = first_item; d.n_items = n_chunks; d.half = h; d.ref_len = ref_len; d.read_len = X.read_len;
+				d.word = word;
+				d.limit = word ? 32767 - std::max(max_mat, 0) : 255 - bias;
+				d.mask_len = X.mask_len; d.cm_off = (int64_t)cm_words;
+				descs.push_back(d);
+				desc_aln.push_back(h ? pt.b : pt.a);
+			}
+			cm_words += ((size_t)ref_len + 3) / 4 * 4;
+		}
+
+		if (e->d_colmax.ensure(cm_words * 4 + 64)) return -1;
+		if (e->run_fill(items, inst, +1, true, false, P, &e->timing.fill_forward_ms)) return -1;
+		e->timing.fill_forward_launches += 1;
+		e->timing.cells_forward += cells;
+
+		/* bookkeeping */
+		if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
+		if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
+		SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
+		e->t_k.start(e->stream);
+		{
+			const int per = SSW_RESOLVE_THREADS / 32;
+			ssw_launch(ssw_resolve_kernel<true>, dim3(((int)descs.size() + per - 1) / per), dim3(SSW_RESOLVE_THREADS), 0, e->stream,
+			           (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(), (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(),
+			           (const uint32_t*)e->d_colmax.as<uint32_t>(), e->d_res.as<SswFillResult>());
+			SSW_CUDA_OK(cudaGetLastError());
+		}
+		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		e->timing.other_launches += 1;
+		std::vector<SswFillResult> res(descs.size());
+		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
+		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+		for (size_t i = 0; i < descs.size(); ++i) { alns[desc_aln[i]].fwd = res[i]; alns[desc_aln[i]].word = word; }
+		k = k_end;
+	}
+	return 0;
+}
+
+/* Begin search (P2, ssw.c:919-936): one reverse item per alignment, early termination at score1. */
+static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>& alns, const std::vector<int64_t>& sel)
+{
+	if (sel.empty()) return 0;
+	struct Key { int inst; int64_t idx; };
+	std::vector<Key> keys(sel.size());
+	for (size_t i = 0; i < sel.size(); ++i) {
+		const Aln& a = alns[sel[i]];
+		const int inst = pick_inst_g32(lp_of(a.fwd.read + 1, a.word));
+		if (inst < 0) return -2;
+		keys[i] = Key{inst, sel[i]};
+	}
+	std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.inst != y.inst ? x.inst < y.inst : x.idx < y.idx; });
+	size_t k = 0;
+	while (k < keys.size()) {
+		const int inst = keys[k].inst;
+		std::vector<SswItem> items;
+		std::vector<SswAlnDesc> descs;
+		std::vector<int64_t> desc_aln;
+		for (; k < keys.size() && keys[k].inst == inst; ++k) {
+			const Aln& a = alns[keys[k].idx];
+			SswItem it;
+			memset(&it, 0, sizeof(it));
+			it.qa.off = (int32_t)e->q_off[a.q]; it.qa.len = a.fwd.read + 1; it.qa.lp = lp_of(it.qa.len, a.word); it.qa.rev = 1;
+			it.ref_off = e->r_off[a.r]; it.ref_len = a.ref_len; it.cend = a.fwd.ref;
+			it.p0 = 0; it.p1 = a.fwd.ref + 1; it.warm = 0; it.term_a = a.fwd.score; it.cm_off = -1;
+			SswAlnDesc d;
+			d.first_item = (int)items.size(); d.n_items = 1; d.half = 0; d.ref_len = it.p1; d.read_len = it.qa.len;
+			d.word = 1; d.limit = 0x7fffffff; d.mask_len = 0; d.cm_off = -1;
+			items.push_back(it);
+			descs.push_back(d);
+			desc_aln.push_back(keys[k].idx);
+		}
+		if (e->run_fill(items, inst, -1, false, true, P, &e->timing.fill_reverse_ms)) return -1;
+		e->timing.other_launches += 1;
+		if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
+		if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
+		SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
+		e->t_k.start(e->stream);
+		{
+			const int per = SSW_RESOLVE_THREADS / 32;
+			ssw_launch(ssw_resolve_kernel<false>, dim3(((int)descs.size() + per - 1) / per), dim3(SSW_RESOLVE_THREADS), 0, e->stream,
+			           (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(), (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(),
+			           (const uint32_t*)nullptr, e->d_res.as<SswFillResult>());
+			SSW_CUDA_OK(cudaGetLastError());
+		}
+		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		e->timing.other_launches += 1;
+		std::vector<SswFillResult> res(descs.size());
+		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
+		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+		for (size_t i = 0; i < descs.size(); ++i) {
+			Aln& a = alns[desc_aln[i]];
+			a.rev_score = res[i].score; a.rev_pos = res[i].ref; a.rev_row = res[i].read;
+		}
+	}
+	return 0;
+}
+
+extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
+                                int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                                ssw_batch_result* results,
+                                uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
+{
+	if (!e || !params || !params->mat || n_pairs < 0 || (n_pairs && !results)) return -1;
+	const ssw_batch_params& P = *params;
+	if (P.n < 1 || P.n > 64) { fprintf(stderr, "[libssw-b200] alphabet size %d not supported (1..64)\n", P.n); return -1; }
+	if ((pair_query == nullptr) != (pair_ref == nullptr)) return -1;
+	int64_t pool_used_local = 0;
+	if (!pool_used) pool_used = &pool_used_local;
+	*pool_used = 0;
+	SSW_CUDA_OK(cudaSetDevice(e->device));
+	memset(&e->timing, 0, sizeof(e->timing));
+	if (n_pairs == 0) return 0;
+	if (P.gap_open <= P.gap_extend) {
+		fprintf(stderr, "[libssw-b200] gap_open <= gap_extend (%d <= %d): this parameter regime is not implemented yet\n", P.gap_open, P.gap_extend);
+		return -3;
+	}
+	e->t_total.start(e->stream);
+
+	/* scoring matrix: bias = |min(mat)| for byte semantics (ssw.c:834-838) */
+	int bias = 0, max_mat = -128;
+	for (int i = 0; i < P.n * P.n; ++i) { if (P.mat[i] < bias) bias = P.mat[i]; if (P.mat[i] > max_mat) max_mat = P.mat[i]; }
+	bias = bias < 0 ? -bias : bias;
+	if (e->d_mat.ensure((size_t)P.n * P.n + 16)) return -1;
+	SSW_CUDA_OK(cudaMemcpyAsync(e->d_mat.p, P.mat, (size_t)P.n * P.n, cudaMemcpyHostToDevice, e->stream));
+	if (e->upload_refs(P.n)) return -1;
+
+	const bool has_byte = P.score_size == 0 || P.score_size == 2, has_word = P.score_size == 1 || P.score_size == 2;
+	std::vector<Aln> alns((size_t)n_pairs);
+	std::vector<int64_t> all((size_t)n_pairs);
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		Aln& a = alns[p];
+		a.q = pair_query ? pair_query[p] : (int32_t)(p / e->n_r);
+		a.r = pair_ref ? pair_ref[p] : (int32_t)(p % e->n_r);
+		if (a.q < 0 || a.q >= e->n_q || a.r < 0 || a.r >= e->n_r) { fprintf(stderr, "[libssw-b200] pair %lld out of range\n", (long long)p); return -1; }
+		a.read_len = (int32_t)(e->q_off[a.q + 1] - e->q_off[a.q]);
+		a.ref_len = e->r_len[a.r];
+		a.mask_len = P.mask_len < 0 ? a.read_len / 2 : P.mask_len;
+		a.word = 0; a.rev_score = 0; a.rev_pos = 0; a.rev_row = 0;
+		memset(&a.fwd, 0, sizeof(a.fwd));
+		all[p] = p;
+		if (a.read_len < 1) { fprintf(stderr, "[libssw-b200] pair %lld: empty query\n", (long long)p); return -1; }
+	}
+	if (!has_byte && !has_word) {
+		fprintf(stderr, "Please call the function ssw_init before ssw_align.\n");
+		for (int64_t p = 0; p < n_pairs; ++p) { memset(&results[p], 0, sizeof(results[p])); results[p].status = 1; results[p].cigar_off = -1; }
+		return 0;
+	}
+
+	/* ---- P1 ---- */
+	int rc = forward_pass(e, P, alns, all, has_byte ? 0 : 1, bias, max_mat);
+	if (rc) return rc;
+	std::vector<int64_t> redo;
+	std::vector<uint8_t> null_result((size_t)n_pairs, 0);
+	if (has_byte) {
+		for (int64_t p = 0; p < n_pairs; ++p)
+			if (alns[p].fwd.overflow == 1) { if (has_word) redo.push_back(p); else null_result[p] = 1; }
+		e->timing.byte_overflows = (int64_t)redo.size();
+		rc = forward_pass(e, P, alns, redo, 1, bias, max_mat);
+		if (rc) return rc;
+	}
+	for (int64_t p = 0; p < n_pairs; ++p)
+		if (!null_result[p] && alns[p].fwd.overflow == 2) {
+			fprintf(stderr, "[libssw-b200] pair %lld: score reaches the 16-bit limit; not supported\n", (long long)p);
+			return -4;
+		}
+
+	/* ---- gating (ssw.c:900-916) and P2 ---- */
+	std::vector<int64_t> need_begin;
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		const Aln& a = alns[p];
+		if (null_result[p] || a.fwd.score <= 0) continue;
+		if (P.flag == 0 || (P.flag == 2 && a.fwd.score < P.filters)) continue;
+		need_begin.push_back(p);
+	}
+	rc = reverse_pass(e, P, alns, need_begin);
+	if (rc) return rc;
+
+	/* ---- assemble the fixed-size records ---- */
+	std::vector<uint8_t> has_begin((size_t)n_pairs, 0);
+	for (int64_t p : need_begin) has_begin[p] = 1;
+	std::vector<SswTbTask> tb;
+	std::vector<int64_t> tb_pair;
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		const Aln& a = alns[p];
+		ssw_batch_result& r = results[p];
+		memset(&r, 0, sizeof(r));
+		r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_off = -1;
+		if (null_result[p]) {
+			fprintf(stderr, "Please set 2 to the score_size parameter of the function ssw_init, otherwise the alignment results will be incorrect.\n");
+			r.status = 1;
+			continue;
+		}
+		if (a.fwd.score <= 0) continue;                                   /* ssw.c:900-903 */
+		r.score1 = (uint16_t)a.fwd.score; r.ref_end1 = a.fwd.ref; r.read_end1 = a.fwd.read;
+		if (a.mask_len >= 15) { r.score2 = (uint16_t)a.fwd.score2; r.ref_end2 = a.fwd.ref2; }
+		else { r.score2 = 0; r.ref_end2 = -1; }
+		if (!has_begin[p]) continue;
+		r.ref_begin1 = a.fwd.ref - a.rev_pos;                              /* scan index 0 == column ref_end1 */
+		r.read_begin1 = a.fwd.read - a.rev_row;                            /* ssw.c:929-930 */
+		if (a.fwd.score > a.rev_score) {
+			fprintf(stderr, "Warning: The alignment path of one pair of sequences may miss a small part. [ssw.c ssw_align]\n");
+			r.flag = 2;
+		}
+		if ((7 & P.flag) == 0 || ((2 & P.flag) != 0 && r.score1 < P.filters) ||
+		    ((4 & P.flag) != 0 && (r.ref_end1 - r.ref_begin1 > P.filterd || r.read_end1 - r.read_begin1 > P.filterd)))
+			continue;                                                      /* ssw.c:938 */
+		SswTbTask t;
+		memset(&t, 0, sizeof(t));
+		t.ref_off = e->r_off[a.r] + r.ref_begin1;
+		t.read_off = e->q_off[a.q] + r.read_begin1;
+		t.ref_len = r.ref_end1 - r.ref_begin1 + 1;
+		t.read_len = r.read_end1 - r.read_begin1 + 1;
+		t.score = r.score1;
+		tb.push_back(t);
+		tb_pair.push_back(p);
+	}
+
+	/* ---- P3 ---- */
+	if (!tb.empty()) {
+		rc = ssw_traceback_run(e->stream, tb, e->d_q.as<int8_t>(), e->d_r.as<int8_t>(), e->d_mat.as<int8_t>(), P.n,
+		                       P.gap_open, P.gap_extend, &e->d_tb, &e->timing.traceback_ms, &e->timing.other_launches,
+		                       [&](size_t i, const uint32_t* words, int32_t len, int failed) -> int {
+			ssw_batch_result& r = results[tb_pair[i]];
+			if (failed) { r.flag = 1; return 0; }                           /* ssw.c:968 */
+			if (!cigar_pool || *pool_used + len > pool_cap) { fprintf(stderr, "[libssw-b200] CIGAR pool too small\n"); return -1; }
+			r.cigar_off = (int32_t)*pool_used; r.cigar_len = len;
+			memcpy(cigar_pool + *pool_used, words, sizeof(uint32_t) * (size_t)len);
+			*pool_used += len;
+			return 0;
+		});
+		if (rc) return rc;
+	}
+	e->timing.total_ms = e->t_total.stop(e->stream);
+	return 0;
+}

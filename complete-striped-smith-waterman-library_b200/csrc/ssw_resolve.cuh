@@ -1,0 +1,89 @@
+/*
+ * ssw_resolve.cuh -- the order-dependent bookkeeping that follows a matrix fill
+ * ("pass B" of SURVEY Appendix A.3).  Replaces, per alignment:
+ *   - the running strict-'>' maximum / end_ref / overflow logic of the SSE2
+ *     loops (src/ssw.c:318-335 byte, :523-537 word),
+ *   - the end_read scan (:342-351, :544-553),
+ *   - the second-best scan outside the mask window (:368-381, :570-583).
+ * One warp per alignment.  Input: the per-item best cells written by the fill
+ * kernel (items are in scan order, so the first item holding the maximum also
+ * holds its first column) and the packed column-maximum row of the pair-task.
+ */
+#ifndef SSW_RESOLVE_CUH
+#define SSW_RESOLVE_CUH
+
+#include "ssw_common.cuh"
+
+#define SSW_RESOLVE_THREADS 128
+
+template <bool SECOND>
+__global__ void __launch_bounds__(SSW_RESOLVE_THREADS)
+ssw_resolve_kernel(const SswAlnDesc* __restrict__ alns, int n_aln,
+                   const SswItemBest* __restrict__ bests, const uint32_t* __restrict__ colmax,
+                   SswFillResult* __restrict__ out)
+{
+	constexpr unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int idx = (int)blockIdx.x * (SSW_RESOLVE_THREADS / 32) + (threadIdx.x >> 5);
+	if (idx >= n_aln) return;
+	const SswAlnDesc d = alns[idx];
+	const int h = d.half;
+
+	/* best cell over the alignment's items: max score, then earliest item */
+	int sc = 0, it_i = 0x7fffffff, pos = 0, row = 0;
+	for (int k = lane; k < d.n_items; k += 32) {
+		const SswItemBest b = bests[d.first_item + k];
+		if (b.score[h] > sc) { sc = b.score[h]; it_i = k; pos = b.pos[h]; row = b.row[h]; }
+	}
+#pragma unroll
+	for (int off = 16; off >= 1; off >>= 1) {
+		const int o_sc = __shfl_xor_sync(FULL, sc, off), o_it = __shfl_xor_sync(FULL, it_i, off);
+		const int o_pos = __shfl_xor_sync(FULL, pos, off), o_row = __shfl_xor_sync(FULL, row, off);
+		if (o_sc > sc || (o_sc == sc && o_it < it_i)) { sc = o_sc; it_i = o_it; pos = o_pos; row = o_row; }
+	}
+
+	SswFillResult r;
+	r.score = sc; r.ref = pos; r.read = row < d.read_len - 1 ? row : d.read_len - 1;
+	r.score2 = 0; r.ref2 = 0; r.overflow = 0; r.pad_[0] = r.pad_[1] = 0;
+	if (sc == 0) { r.ref = d.word ? 0 : -1; r.read = 0; }
+	if (sc >= d.limit) { r.overflow = d.word ? 2 : 1; if (!d.word) r.score = 255; }
+
+	if (SECOND && sc > 0 && !r.overflow && d.cm_off >= 0) {
+		/* columns [0, e1) and [e2, refLen), smallest index of the largest value, values must be > 0 */
+		const int e1 = max(pos - d.mask_len, 0);
+		const int e2 = min(pos + d.mask_len, d.ref_len) + (d.word ? 0 : 1);
+		const uint32_t* cm = colmax + d.cm_off;
+		int v2 = 0, i2 = 0;
+		const int n4 = (d.ref_len + 3) / 4;
+		for (int q = lane; q < n4; q += 32) {
+			const int c0 = q * 4;
+			if (c0 + 3 >= e1 && c0 < e2) {
+				/* block touches the masked window: element-wise test */
+				const uint4 w = *reinterpret_cast<const uint4*>(cm + c0);
+				const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const int c = c0 + j, v = half_of(ww[j], h);
+					if (c < d.ref_len && (c < e1 || c >= e2) && v > v2) { v2 = v; i2 = c; }
+				}
+			} else {
+				const uint4 w = *reinterpret_cast<const uint4*>(cm + c0);
+				const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const int c = c0 + j, v = half_of(ww[j], h);
+					if (c < d.ref_len && v > v2) { v2 = v; i2 = c; }
+				}
+			}
+		}
+#pragma unroll
+		for (int off = 16; off >= 1; off >>= 1) {
+			const int o_v = __shfl_xor_sync(FULL, v2, off), o_i = __shfl_xor_sync(FULL, i2, off);
+			if (o_v > v2 || (o_v == v2 && o_v > 0 && o_i < i2)) { v2 = o_v; i2 = o_i; }
+		}
+		r.score2 = v2; r.ref2 = i2;
+	}
+	if (lane == 0) out[idx] = r;
+}
+
+#endif /* SSW_RESOLVE_CUH */

@@ -1,0 +1,111 @@
+/*
+ * ssw_batch.h -- batched C ABI of the B200-native aligner.
+ *
+ * The reference's API aligns one (query, reference) pair per blocking call
+ * (ssw.h:126-134); its CLI loops over reads x references around that call
+ * (main.c:462-532).  One pair exposes far too little parallelism for a GPU,
+ * so the same computation is offered over a whole batch of independent pairs.
+ * Every pair's answer is field-for-field what ssw_init(score_size) +
+ * ssw_align(...) of ssw.h returns for that pair.
+ *
+ * All pointers are plain host pointers to caller-owned memory; no type of any
+ * framework appears in this interface.  Functions return 0 on success and a
+ * negative value on error (message on stderr).  There is no CPU compute path:
+ * without a usable CUDA device ssw_engine_create fails.
+ */
+#ifndef SSW_BATCH_H
+#define SSW_BATCH_H
+
+#include <stdint.h>
+#include "ssw.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssw_engine ssw_engine;
+
+/* Scoring and reporting parameters shared by all pairs of a batch; same meaning
+ * as the arguments of ssw_init / ssw_align (ssw.h:86, :126-134). */
+typedef struct {
+	const int8_t* mat;      /* n*n scores, row = reference code, column = query code */
+	int32_t n;              /* alphabet size (codes are 0..n-1), n <= 64 */
+	uint8_t gap_open;       /* weight_gapO */
+	uint8_t gap_extend;     /* weight_gapE */
+	uint8_t flag;           /* ssw_align flag */
+	uint16_t filters;       /* ssw_align filters */
+	int32_t filterd;        /* ssw_align filterd */
+	int32_t mask_len;       /* ssw_align maskLen; negative: readLen / 2 per query (the CLI's choice, main.c:465) */
+	int8_t score_size;      /* ssw_init score_size: 0 byte, 1 word, 2 byte then word */
+} ssw_batch_params;
+
+/* Fixed-size per-pair result; same fields as s_align with the CIGAR stored out of line. */
+typedef struct {
+	uint16_t score1, score2;
+	int32_t ref_begin1, ref_end1, read_begin1, read_end1, ref_end2;
+	int32_t cigar_off;      /* offset of this pair's words in the batch CIGAR pool, -1 if none */
+	int32_t cigar_len;
+	uint16_t flag;          /* s_align.flag */
+	uint16_t status;        /* 0 ok; 1: ssw_align would have returned NULL (byte overflow with score_size 0) */
+} ssw_batch_result;
+
+/* Create an engine bound to CUDA device `device` (-1: current device). NULL on failure. */
+ssw_engine* ssw_engine_create(int device);
+void ssw_engine_destroy(ssw_engine* e);
+
+/* Name of the device the engine runs on ("" if none). */
+const char* ssw_engine_device_name(const ssw_engine* e);
+
+/*
+ * Make a set of sequences resident in device memory (host -> device copy).
+ *   queries / refs     concatenated codes
+ *   query_off/ref_off  n+1 offsets into the concatenations
+ * Replaces any previously resident set.
+ */
+int ssw_engine_set_sequences(ssw_engine* e,
+                             int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                             int32_t n_refs, const int8_t* refs, const int64_t* ref_off);
+
+/*
+ * Align pairs of resident sequences.
+ *   pair_query / pair_ref   n_pairs indices; both NULL: the full grid, pair p = query p / n_refs x ref p % n_refs
+ *   results                 n_pairs records (host memory)
+ *   cigar_pool, pool_cap    optional pool receiving the CIGAR words (may be NULL when flag requests no CIGAR);
+ *   pool_used               receives the number of words written
+ */
+int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
+                     int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                     ssw_batch_result* results,
+                     uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used);
+
+/*
+ * Convenience: set_sequences + align + conversion to heap s_align records
+ * (each to be released with align_destroy; NULL where ssw_align would return NULL).
+ */
+int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
+                    int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                    int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
+                    int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                    s_align** out);
+
+/* Device-time breakdown of the last ssw_engine_align call (CUDA events on the engine's stream), in ms. */
+typedef struct {
+	float fill_forward_ms;   /* matrix fill kernels, forward pass (incl. byte->word reruns) */
+	float resolve_ms;        /* bookkeeping kernels */
+	float fill_reverse_ms;   /* begin-search fill kernels */
+	float traceback_ms;      /* banded traceback kernels */
+	float total_ms;          /* first launch to last completion, incl. host planning in between */
+	int64_t fill_forward_launches, other_launches;
+	int64_t cells_forward;   /* DP cells computed by the forward fill kernels (incl. warm-up and pad rows) */
+	int64_t byte_overflows;  /* pairs re-run with word semantics */
+} ssw_engine_timing;
+int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t);
+
+/* Tuning knobs, mostly for tests: "chunk" (reference chunk length in columns, 0 = automatic). */
+int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SSW_BATCH_H */

@@ -1,0 +1,50 @@
+"""CPU test: the shipped CUDA library loads and exports every symbol that include/*.h
+declares (plus the two helpers the reference's libssw.so leaks).  No compute calls."""
+import ctypes as ct
+import os
+import re
+import subprocess
+
+import pytest
+
+import common as C
+
+DECLARED = ["ssw_init", "init_destroy", "ssw_align", "align_destroy", "mark_mismatch", "encoded_ops",
+            "ssw_engine_create", "ssw_engine_destroy", "ssw_engine_device_name", "ssw_engine_set_sequences",
+            "ssw_engine_align", "ssw_align_batch", "ssw_engine_last_timing", "ssw_engine_set_option"]
+LEAKED_BY_REFERENCE = ["add_cigar", "store_previous_m"]       # non-static in ssw.c:984,994
+
+
+def _declared_in_headers():
+    names = set()
+    for h in ("ssw.h", "ssw_batch.h"):
+        txt = open(os.path.join(C.ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b([a-z_]+[a-z0-9_]*)\s*\(", txt):
+            if not re.search(r"static\s+inline[^;{]*\b%s\s*\($" % m.group(1), txt[: m.end()].split(";")[-1]):
+                names.add(m.group(1))
+    return names
+
+
+def test_headers_and_list_agree():
+    found = _declared_in_headers()
+    for s in DECLARED:
+        if s != "encoded_ops":
+            assert s in found, s
+
+
+@pytest.mark.skipif(not os.path.exists(C.LIB_OURS), reason="libssw.so not built yet (python __graft_entry__.py)")
+def test_library_exports_every_declared_symbol():
+    lib = ct.CDLL(C.LIB_OURS)
+    for s in DECLARED + LEAKED_BY_REFERENCE:
+        assert hasattr(lib, s), "libssw.so does not export %s" % s
+    ops = (ct.c_uint8 * 128).in_dll(lib, "encoded_ops")
+    assert [ops[ord(c)] for c in "MIDNSHP=X"] == list(range(9))
+    out = subprocess.run(["nm", "-D", "--defined-only", C.LIB_OURS], capture_output=True, text=True).stdout
+    assert " T ssw_align" in out and " T ssw_engine_align" in out
+
+
+@pytest.mark.skipif(not os.path.exists(C.LIB_OURS), reason="libssw.so not built yet")
+def test_product_does_not_link_the_oracle():
+    out = subprocess.run(["nm", "-D", C.LIB_OURS], capture_output=True, text=True).stdout
+    assert "oracle_" not in out and "cuemu" not in out

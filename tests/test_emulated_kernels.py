@@ -1,0 +1,83 @@
+"""CPU tests of the PRODUCT's kernel and engine sources, compiled for the fiber emulator
+(tests/cuda_emu, test infrastructure) and compared with the oracle.  This is how kernel
+logic is validated in the GPU-less build container; the same comparisons run against the
+real CUDA library in test_gpu_parity.py.  libssw_emu.so is never used by the product.
+"""
+import importlib.util
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common as C
+from test_oracle import golden_inputs, random_case, run_golden
+
+EMU_DIR = os.path.join(C.ROOT, "tests", "cuda_emu")
+
+
+def _pkg():
+    spec = importlib.util.spec_from_file_location("ssw_b200_lib", os.path.join(C.PKG, "ssw_lib.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    return C.SswLib(os.path.join(EMU_DIR, "libssw_emu.so"))
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return C.load_oracle()
+
+
+def test_emulated_goldens(emu, capfd):
+    with open(os.path.join(C.GOLDEN, "goldens.json")) as f:
+        goldens = json.load(f)
+    for case in goldens:
+        if "refs_npz" in case:
+            continue                       # 1 Mbp reference: GPU test only
+        limit = 6 if len(case["reads"]) > 6 else None
+        assert run_golden(emu, case, limit) == []
+
+
+def test_emulated_random_vs_oracle(emu, oracle, capfd):
+    rng = np.random.default_rng(424242)
+    bad = []
+    n = 0
+    while n < 120:
+        c = random_case(rng)
+        if c["gapO"] <= c["gapE"]:
+            continue
+        n += 1
+        d = C.diff_results(emu.align(**c), oracle.align(**c))
+        if d:
+            bad.append((n, d))
+    assert bad == []
+
+
+def test_emulated_chunked_reference(oracle, capfd):
+    """Reference chunking with warm-up overlap (forced small chunks) must not change any field."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("chunk", 64)
+    rng = np.random.default_rng(99)
+    mat = C.dna_matrix(2, 2)
+    ref = rng.integers(0, 4, size=1500).astype(np.int8)
+    reads = [C.mutate_read(rng, ref, int(rng.integers(0, 1400)), int(rng.integers(20, 41)), 0.1, 0.02, 0.02) for _ in range(7)]
+    reads.append(rng.integers(0, 4, size=33).astype(np.int8))
+    eng.set_sequences(reads, [ref])
+    for flag in (0, 0x0f):
+        res, pool = eng.align(mat, 5, 3, 2, flag=flag, filterd=32767, mask_len=15, score_size=2)
+        for i, q in enumerate(reads):
+            exp = oracle.align(q, ref, mat, 5, 3, 2, flag, 0, 32767, 15, 2)
+            r = res[i]
+            got = {k: int(r[k]) for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
+            got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
+            assert C.diff_results(got, exp) == [], (flag, i)
+    eng.close()
