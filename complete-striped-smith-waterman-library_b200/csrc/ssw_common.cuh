@@ -93,8 +93,7 @@ struct SswItemBest {
 	int32_t score[2];
 	int32_t pos[2];     /* scan index */
 	int32_t row[2];
-	int32_t stopped;    /* reverse pass: 1 if the early-termination column was reached */
-	int32_t pad_;
+	int32_t p0, p1;     /* the item's counted scan range, copied for the resolve kernel */
 };
 
 /* One alignment as the resolve kernel sees it. */

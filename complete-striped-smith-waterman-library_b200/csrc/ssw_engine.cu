@@ -24,25 +24,39 @@
 #include "ssw_traceback.cuh"
 #include "../../include/ssw_batch.h"
 
+#include <chrono>
 namespace {
+
+static bool ssw_trace_on() { static int v = -1; if (v < 0) { const char* e = getenv("SSW_TRACE"); v = e && *e && *e != '0'; } return v != 0; }
+struct Trace {
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	void lap(const char* what) {
+		if (!ssw_trace_on()) return;
+		auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[libssw-b200 trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
 
 /* kernel instance = (lanes per group, rows per lane); rows covered = G*R */
 struct Inst { int G, R; };
 static const Inst kInst[] = {
-	{8, 4}, {8, 5}, {8, 8}, {8, 10}, {16, 8}, {16, 10}, {32, 8}, {32, 10}, {32, 16},
+	{8, 4}, {8, 5}, {8, 8}, {8, 10}, {16, 8}, {16, 10}, {32, 8}, {32, 10}, {32, 16}, {8, 20}, {32, 5},
 };
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 static const int kMaxRows = 512;
 
+static int g_force_inst = -1;      /* experiment knob ("inst" option): use this instance whenever it covers the query */
 static int pick_inst(int lp)
 {
-	for (int i = 0; i < kNumInst; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
+	if (g_force_inst >= 0 && g_force_inst < kNumInst && kInst[g_force_inst].G * kInst[g_force_inst].R >= lp) return g_force_inst;
+	for (int i = 0; i < 9; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
 	return -1;
 }
 /* reverse pass: one alignment per warp */
 static int pick_inst_g32(int lp)
 {
-	for (int i = 0; i < kNumInst; ++i) if (kInst[i].G == 32 && kInst[i].G * kInst[i].R >= lp) return i;
+	for (int i = 0; i < 9; ++i) if (kInst[i].G == 32 && kInst[i].G * kInst[i].R >= lp) return i;
 	return -1;
 }
 
@@ -128,6 +142,8 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, b
 	case 6: rc = launch_fill<32, 8>(this, n_items, dir, write_cm, term, P); break;
 	case 7: rc = launch_fill<32, 10>(this, n_items, dir, write_cm, term, P); break;
 	case 8: rc = launch_fill<32, 16>(this, n_items, dir, write_cm, term, P); break;
+	case 9: rc = launch_fill<8, 20>(this, n_items, dir, write_cm, term, P); break;
+	case 10: rc = launch_fill<32, 5>(this, n_items, dir, write_cm, term, P); break;
 	default: break;
 	}
 	*ms_acc += t_k.stop(stream);
@@ -177,6 +193,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 {
 	if (!e || !name) return -1;
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
+	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;
 }
@@ -254,6 +271,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
                         int word, int bias, int max_mat)
 {
 	if (sel.empty()) return 0;
+	Trace tr;
 	/* order: kernel instance, reference, then query length so that partners are alike */
 	struct Key { int inst; int32_t r; int32_t lp; int64_t idx; };
 	std::vector<Key> keys(sel.size());
@@ -351,8 +369,10 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			cm_words += ((size_t)ref_len + 3) / 4 * 4;
 		}
 
+		tr.lap("forward: plan");
 		if (e->d_colmax.ensure(cm_words * 4 + 64)) return -1;
 		if (e->run_fill(items, inst, +1, true, false, P, &e->timing.fill_forward_ms)) return -1;
+		tr.lap("forward: fill (copy+kernel)");
 		e->timing.fill_forward_launches += 1;
 		e->timing.cells_forward += cells;
 
@@ -374,6 +394,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
 		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
 		for (size_t i = 0; i < descs.size(); ++i) { alns[desc_aln[i]].fwd = res[i]; alns[desc_aln[i]].word = word; }
+		tr.lap("forward: resolve + d2h");
 		k = k_end;
 	}
 	return 0;

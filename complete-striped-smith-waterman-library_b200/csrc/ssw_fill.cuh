@@ -44,6 +44,39 @@ __host__ __device__ static __forceinline__ int ssw_prof_slot(int k, int lane)
 	return k < 4 * A ? (k / 4) * 128 + lane * 4 + (k % 4) : A * 128 + lane * REM + (k - 4 * A);
 }
 
+/* Shared-memory reads of the profile.  On the device they are issued as ld.shared from a 32-bit shared
+ * address (no generic-address conversion inside the sweep); the emulator build uses plain loads. */
+#ifdef SSW_CPU_EMU
+typedef const uint32_t* ssw_saddr;
+__device__ static __forceinline__ ssw_saddr ssw_sbase(const uint32_t* p) { return p; }
+__device__ static __forceinline__ ssw_saddr ssw_sadd(ssw_saddr a, int words) { return a + words; }
+__device__ static __forceinline__ uint4 ssw_lds128(ssw_saddr a) { return *reinterpret_cast<const uint4*>(a); }
+__device__ static __forceinline__ uint2 ssw_lds64(ssw_saddr a) { return *reinterpret_cast<const uint2*>(a); }
+__device__ static __forceinline__ uint32_t ssw_lds32(ssw_saddr a) { return *a; }
+#else
+typedef uint32_t ssw_saddr;
+__device__ static __forceinline__ ssw_saddr ssw_sbase(const uint32_t* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ static __forceinline__ ssw_saddr ssw_sadd(ssw_saddr a, int words) { return a + 4u * (uint32_t)words; }
+__device__ static __forceinline__ uint4 ssw_lds128(ssw_saddr a)
+{
+	uint4 v;
+	asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ static __forceinline__ uint2 ssw_lds64(ssw_saddr a)
+{
+	uint2 v;
+	asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+	return v;
+}
+__device__ static __forceinline__ uint32_t ssw_lds32(ssw_saddr a)
+{
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+#endif
+
 /* shared-memory bytes the fill kernel needs for an alphabet of n letters */
 template <int R>
 static inline size_t ssw_fill_smem_bytes(int n) { return (size_t)SSW_FILL_WARPS * (size_t)(n + 1) * 32 * R * sizeof(uint32_t); }
@@ -56,7 +89,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 uint32_t* __restrict__ colmax, SswItemBest* __restrict__ bests)
 {
 	static_assert(G == 8 || G == 16 || G == 32, "group width");
-	static_assert(R % 4 != 3 && R >= 1 && R <= 16, "rows per lane");
+	static_assert(R % 4 != 3 && R >= 1 && R <= 20, "rows per lane");
 	static_assert(!TERM || G == 32, "early termination is per warp");
 	constexpr int GPW = 32 / G;                 /* groups per warp */
 	constexpr int A4 = R / 4, REM = R % 4;
@@ -102,7 +135,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	__syncwarp();
 
 	/* ---- sweep ---- */
-	const int8_t* rp = refs + it.ref_off;               /* reference column 0 */
+	const uint8_t* rp = reinterpret_cast<const uint8_t*>(refs) + it.ref_off;   /* reference column 0 */
 	const uint32_t negO = pack2(-gapO, -gapO), negE = pack2(-gapE, -gapE);
 	int sL = (it.p0 - it.warm - (G - 1)) & ~3;          /* scan position of the group's last lane, multiple of 4 */
 	int n_body = live && it.p1 > sL ? (it.p1 - sL + 3) / 4 : 0;
@@ -113,6 +146,16 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	int col = DIR > 0 ? sL + (G - 1 - t) : it.cend - (sL + (G - 1 - t));
 	const int col_hi = it.ref_len + SSW_REF_PAD - 4, col_lo = -SSW_REF_PAD + 3;
 	if (DIR > 0) col = min(col, col_hi); else col = max(col, col_lo);
+	int sp0 = sL + (G - 1 - t);                         /* this lane's scan position at step j = 0 */
+
+	/* per-lane shared-memory cursors: rows 0..4*A4-1 as uint4 segments, the tail behind them */
+	const ssw_saddr pbase = ssw_sadd(ssw_sbase(prof), lane * 4);
+	const ssw_saddr ptail = ssw_sadd(ssw_sbase(prof), A4 * 128 + lane * REM);
+	uint32_t top_keep = t == 0 ? 0u : 1u;               /* lane 0 of a group takes zeros from above (multiplied in: FMA pipe) */
+	const uint8_t* lptr = rp + col;                     /* letter cursor, advanced together with col */
+#ifndef SSW_CPU_EMU
+	asm volatile("" : "+r"(top_keep) : : "memory");     /* opaque 0/1 so that the masking stays a multiply */
+#endif
 
 	uint32_t Hd[R], E[R];
 #pragma unroll
@@ -124,27 +167,27 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 
 	for (int body = 0; body < n_body; ++body) {
 		uint32_t cmv[4];
+		const bool maybe_counted = sp0 + 3 >= it.p0 && sp0 < it.p1;   /* this body touches the counted range */
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			/* values crossing the lane boundary */
-			uint32_t inH = __shfl_up_sync(FULL, outH, 1, G);
-			uint32_t inF = __shfl_up_sync(FULL, outF, 1, G);
-			uint32_t inC = __shfl_up_sync(FULL, outC, 1, G);
-			if (t == 0) { inH = 0; inF = 0; inC = 0; }
+			const uint32_t inH = __shfl_up_sync(FULL, outH, 1, G) * top_keep;
+			const uint32_t inF = __shfl_up_sync(FULL, outF, 1, G) * top_keep;
+			const uint32_t inC = __shfl_up_sync(FULL, outC, 1, G) * top_keep;
 
 			/* reference letter of this lane's scan position and its profile rows */
-			int letter = (int)rp[col + DIR * j];
-			if (DIR < 0) { if (sL + (G - 1 - t) + j < 0) letter = n; }
-			const uint32_t* pl = prof + letter * letter_stride;
+			int letter = (int)lptr[DIR * j];
+			if (DIR < 0) { if (sp0 + j < 0) letter = n; }
+			const ssw_saddr pl = ssw_sadd(pbase, letter * letter_stride);
 			uint32_t s[R];
 #pragma unroll
 			for (int q = 0; q < A4; ++q) {
-				const uint4 v = *reinterpret_cast<const uint4*>(pl + q * 128 + lane * 4);
+				const uint4 v = ssw_lds128(ssw_sadd(pl, q * 128));
 				s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
 			}
-			if (REM == 1) s[4 * A4] = pl[A4 * 128 + lane];
+			if (REM == 1) s[4 * A4] = ssw_lds32(ssw_sadd(ptail, letter * letter_stride));
 			if (REM == 2) {
-				const uint2 v = *reinterpret_cast<const uint2*>(pl + A4 * 128 + lane * 2);
+				const uint2 v = ssw_lds64(ssw_sadd(ptail, letter * letter_stride));
 				s[4 * A4] = v.x; s[4 * A4 + 1] = v.y;
 			}
 
@@ -171,8 +214,11 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 
 			/* running best of this lane (strict increase only; rare path) */
 			const uint32_t nb = __vmaxs2(best, m);
-			if (nb != best) {
-				const int sp = sL + (G - 1 - t) + j;
+			if (nb != best && maybe_counted) {
+				int sp = sp0 + j;
+#ifndef SSW_CPU_EMU
+				asm volatile("" : "+r"(sp));                /* keep the range test inside the rare path */
+#endif
 				if (sp >= it.p0 && sp < it.p1) {
 					if (half_of(nb, 0) > half_of(best, 0)) {
 						bpos0 = sp;
@@ -205,7 +251,12 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		}
 
 		sL += 4;
-		if (DIR > 0) col = min(col + 4, col_hi); else col = max(col - 4, col_lo);
+		sp0 += 4;
+		{
+			const int ncol = DIR > 0 ? min(col + 4, col_hi) : max(col - 4, col_lo);
+			lptr += ncol - col;
+			col = ncol;
+		}
 	}
 
 	/* ---- reduce the group's lanes to one record per half: max score, then first position, then smallest row ---- */
@@ -217,12 +268,11 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		if (o_sc0 > sc0 || (o_sc0 == sc0 && (o_p0 < bpos0 || (o_p0 == bpos0 && o_r0 < brow0)))) { sc0 = o_sc0; bpos0 = o_p0; brow0 = o_r0; }
 		if (o_sc1 > sc1 || (o_sc1 == sc1 && (o_p1 < bpos1 || (o_p1 == bpos1 && o_r1 < brow1)))) { sc1 = o_sc1; bpos1 = o_p1; brow1 = o_r1; }
 	}
-	if (TERM) stopped = __any_sync(FULL, stopped);
 	if (live && t == 0) {
 		SswItemBest b;
 		b.score[0] = sc0; b.pos[0] = bpos0; b.row[0] = brow0;
 		b.score[1] = sc1; b.pos[1] = bpos1; b.row[1] = brow1;
-		b.stopped = stopped; b.pad_ = 0;
+		b.p0 = it.p0; b.p1 = it.p1;
 		bests[item_idx] = b;
 	}
 }

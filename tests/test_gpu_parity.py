@@ -1,0 +1,211 @@
+"""GPU parity tests (run on the B200 box): the CUDA library, called through its C ABI,
+must return bit-identical s_align records to the oracle (and to the unmodified reference
+library oracle/_ref/libssw_ref.so when that prebuilt checker travelled with the snapshot).
+Nothing here reads /root/reference."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common as C
+from test_oracle import golden_inputs, random_case, run_golden
+
+pytestmark = pytest.mark.gpu
+
+FIELDS8 = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")
+
+
+def _pkg():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ssw_b200_lib", os.path.join(C.PKG, "ssw_lib.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def ours():
+    assert os.path.exists(C.LIB_OURS), "libssw.so missing: the CUDA extension must be built in-tree (no fallback)"
+    return C.load_ours()
+
+
+@pytest.fixture(scope="module")
+def checker():
+    """The strongest checker available: the compiled reference if it travelled, else the oracle port."""
+    return C.load_ref() if C.have_ref() else C.load_oracle()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return C.load_oracle()
+
+
+@pytest.fixture(scope="module")
+def engine():
+    L = _pkg()
+    e = L.BatchAligner(device=0)
+    yield e
+    e.close()
+
+
+def batch_dict(res, pool, i):
+    r = res[i]
+    d = {k: int(r[k]) for k in FIELDS8}
+    d["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
+    return d
+
+
+def test_goldens_through_ssw_h(ours, capfd):
+    """Every frozen golden (demo/old.txt, README sample, config 1, protein, example.c) through ssw_init/ssw_align."""
+    with open(os.path.join(C.GOLDEN, "goldens.json")) as f:
+        goldens = json.load(f)
+    for case in goldens:
+        limit = 10 if "refs_npz" in case else None
+        assert run_golden(ours, case, limit) == [], case["name"]
+
+
+def test_demo_golden_1M_batched(engine):
+    """The reference's shipped regression golden (100 x 54 bp vs 1 Mbp, demo/old.txt) through the batch ABI."""
+    with open(os.path.join(C.GOLDEN, "goldens.json")) as f:
+        case = [c for c in json.load(f) if "refs_npz" in c][0]
+    mat, refs, reads = golden_inputs(case)
+    engine.set_sequences(reads, refs)
+    res, pool = engine.align(mat, 5, 3, 1, flag=0, mask_len=-1, score_size=2)
+    for i, exp in enumerate(case["expected"]):
+        assert C.diff_results(batch_dict(res, pool, i), exp) == [], i
+
+
+def test_random_pairs_vs_checker(ours, checker, capfd):
+    rng = np.random.default_rng(31337)
+    bad = []
+    n = 0
+    while n < 1500:
+        c = random_case(rng)
+        if c["gapO"] <= c["gapE"]:
+            continue
+        n += 1
+        a = ours.align(mark=True, **c)
+        b = checker.align(mark=True, **c)
+        d = C.diff_results(a, b)
+        if a and b and (a.get("nm"), a.get("cigar_marked")) != (b.get("nm"), b.get("cigar_marked")):
+            d.append(("marked", a.get("cigar_marked"), b.get("cigar_marked")))
+        if d:
+            bad.append((n, d))
+    assert bad == []
+
+
+@pytest.mark.parametrize("flag", [0, 8, 2, 0x0f])
+def test_config2_shape_reduced(engine, checker, flag, capfd):
+    """Config 2 shape at a size the checker finishes in seconds: 150 bp reads vs a 300 kbp reference, all flags."""
+    ref, reads = C.make_dna_workload(300_000, 96, 150, seed_ref=1001, seed_reads=2002)
+    mat = C.dna_matrix(2, 2)
+    engine.set_sequences(reads, [ref])
+    res, pool = engine.align(mat, 5, 3, 1, flag=flag, filters=0, filterd=32767, mask_len=75, score_size=2)
+    n_check = len(reads) if C.have_ref() else 12
+    for i in range(n_check):
+        exp = checker.align(reads[i], ref, mat, 5, 3, 1, flag, 0, 32767, 75, 2)
+        assert C.diff_results(batch_dict(res, pool, i), exp) == [], (flag, i)
+
+
+def test_config2_full_size_properties(engine, checker, capfd):
+    """BASELINE config 2 at full size (1,000 x 150 bp vs 5 Mbp): chunk-size invariance of every field, agreement of a
+    fixed subsample with the checker, and the score bounds the workload model implies."""
+    ref, reads = C.make_dna_workload(5_000_000, 1000, 150, seed_ref=1001, seed_reads=2002)
+    mat = C.dna_matrix(2, 2)
+    engine.set_sequences(reads, [ref])
+    res_a, _ = engine.align(mat, 5, 3, 1, flag=0, mask_len=75, score_size=2)
+    engine.set_option("chunk", 20000)
+    res_b, _ = engine.align(mat, 5, 3, 1, flag=0, mask_len=75, score_size=2)
+    engine.set_option("chunk", 0)
+    assert (res_a == res_b).all()
+    assert int(res_a["score1"].max()) <= 300 and int(res_a["score1"].min()) > 0
+    assert (res_a["ref_end1"] < 5_000_000).all() and (res_a["read_end1"] < 150).all()
+    assert engine.timing()["byte_overflows"] >= 0
+    sub = list(range(0, 1000, 64)) if C.have_ref() else [0]
+    for i in sub:
+        exp = checker.align(reads[i], ref, mat, 5, 3, 1, 0, 0, 0, 75, 2)
+        got = {k: int(res_a[i][k]) for k in FIELDS8}
+        got["cigar"] = []
+        assert C.diff_results(got, exp) == [], i
+
+
+def test_protein_word_path(engine, checker, capfd):
+    """Config 4 shape reduced: BLOSUM50, 300 aa queries x 400 aa targets, score_size 1 (word semantics)."""
+    rng = np.random.default_rng(4004)
+    queries = [rng.integers(0, 20, size=300).astype(np.int8) for _ in range(12)]
+    targets = []
+    for t in range(40):
+        s = rng.integers(0, 20, size=400).astype(np.int8)
+        if t % 4 == 0:
+            q = queries[int(rng.integers(0, len(queries)))]
+            seg = q[50:250].copy()
+            m = rng.random(len(seg)) < 0.2
+            seg[m] = rng.integers(0, 20, size=int(m.sum()))
+            s[100:300] = seg
+        targets.append(s)
+    engine.set_sequences(queries, targets)
+    res, pool = engine.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
+    k = 0
+    for q in queries:
+        for t in targets:
+            exp = checker.align(q, t, C.BLOSUM50, 24, 3, 1, 0, 0, 0, 150, 1)
+            assert C.diff_results(batch_dict(res, pool, k), exp) == [], k
+            k += 1
+
+
+def test_byte_overflow_falls_back_to_word(engine, ours, checker, capfd):
+    """Scores >= 255 - bias: score_size 2 re-runs with word semantics (ssw.c:883-886); score_size 0 returns NULL (:887-890)."""
+    rng = np.random.default_rng(5)
+    ref = rng.integers(0, 4, size=4000).astype(np.int8)
+    reads = [C.mutate_read(rng, ref, int(rng.integers(0, 3000)), 400, 0.03, 0.005, 0.005) for _ in range(8)]
+    reads.append(rng.integers(0, 4, size=400).astype(np.int8))
+    mat = C.dna_matrix(2, 2)
+    engine.set_sequences(reads, [ref])
+    for flag in (0, 0x0f):
+        res, pool = engine.align(mat, 5, 3, 1, flag=flag, filterd=32767, mask_len=200, score_size=2)
+        assert engine.timing()["byte_overflows"] >= 8
+        for i, q in enumerate(reads):
+            exp = checker.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, 200, 2)
+            assert C.diff_results(batch_dict(res, pool, i), exp) == [], (flag, i)
+    assert ours.align(reads[0], ref, mat, 5, 3, 1, 0, 0, 0, 200, score_size=0) is None
+    assert checker.align(reads[0], ref, mat, 5, 3, 1, 0, 0, 0, 200, score_size=0) is None
+
+
+def test_edge_cases(ours, checker, capfd):
+    """Length-1 sequences, all-N queries, zero score, maskLen < 15, ragged batch."""
+    mat = C.dna_matrix(2, 2)
+    cases = [
+        (np.array([0], np.int8), np.array([0], np.int8)),
+        (np.array([0], np.int8), np.array([1], np.int8)),
+        (np.full(40, 4, np.int8), np.arange(100, dtype=np.int8) % 4),
+        (np.arange(17, dtype=np.int8) % 4, np.array([2], np.int8)),
+        (np.zeros(16, np.int8), np.zeros(16, np.int8)),
+        (np.zeros(15, np.int8), np.zeros(400, np.int8)),
+    ]
+    for q, r in cases:
+        for flag in (0, 1, 0x0f):
+            for ml in (5, 15):
+                a = ours.align(q, r, mat, 5, 3, 1, flag, 0, 32767, ml, 2)
+                b = checker.align(q, r, mat, 5, 3, 1, flag, 0, 32767, ml, 2)
+                assert C.diff_results(a, b) == [], (len(q), len(r), flag, ml)
+
+
+def test_unmodified_reference_consumers_on_our_library(tmp_path, capfd):
+    """The reference's own ssw_test / example_c / example_cpp (built UNMODIFIED in the build container against our
+    libssw.so) reproduce the outputs the reference produces with its own ssw.c (frozen in consumer_outputs.json)."""
+    gold = os.path.join(C.GOLDEN, "consumer_outputs.json")
+    bindir = os.path.join(C.ORACLE_DIR, "_ref")
+    if not (os.path.exists(gold) and os.path.exists(os.path.join(bindir, "ssw_test_b200"))):
+        pytest.skip("prebuilt consumers not present")
+    with open(gold) as f:
+        G = json.load(f)
+    for name, seqs in G["files"].items():
+        (tmp_path / name).write_text(seqs)
+    for run in G["runs"]:
+        exe = os.path.join(bindir, run["exe"] + "_b200")
+        args = [a if not a.endswith((".fa", ".fq", ".fastq")) else str(tmp_path / a) for a in run["args"]]
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        got = "\n".join(l for l in out.stdout.splitlines() if not l.startswith("CPU time"))
+        assert got == run["stdout"], (run["exe"], run["args"])
