@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inst", type=int, default=-1, help="experiment: force a fill-kernel instance")
     ap.add_argument("--chunk", type=int, default=0, help="experiment: reference chunk length")
+    ap.add_argument("--mode", type=int, default=-1, help="experiment: fill arithmetic (0 all-DPX, 1 biased + IMAD)")
     return ap.parse_args()
 
 
@@ -187,6 +188,8 @@ def main():
         eng.set_option("inst", args.inst)
     if args.chunk:
         eng.set_option("chunk", args.chunk)
+    if args.mode >= 0:
+        eng.set_option("mode", args.mode)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
     def barrier():

@@ -46,6 +46,7 @@ static const Inst kInst[] = {
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 static const int kMaxRows = 512;
 
+static int g_fill_mode = 0;        /* fill-kernel arithmetic ("mode" option): 0 all-DPX, 1 biased with IMAD adds */
 static int g_force_inst = -1;      /* experiment knob ("inst" option): use this instance whenever it covers the query */
 static int pick_inst(int lp)
 {
@@ -108,7 +109,7 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, bool write_cm, bool 
 	SswItemBest* bests = e->d_bests.as<SswItemBest>();
 #define SSW_FILL_GO(DIR, CM, TERM)                                                                               \
 	do {                                                                                                         \
-		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM>;                                                        \
+		auto kern = g_fill_mode == 1 ? ssw_fill_kernel<G, R, DIR, CM, TERM, 1> : ssw_fill_kernel<G, R, DIR, CM, TERM, 0>; \
 		if (smem > 48 * 1024)                                                                                    \
 			SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
 		ssw_launch(kern, dim3(grid), dim3(SSW_FILL_THREADS), smem, e->stream, items, n_items, q, r, mat, (int)P.n, \
@@ -129,7 +130,9 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, b
 	if (n_items == 0) return 0;
 	if (d_items.ensure(sizeof(SswItem) * items.size())) return -1;
 	if (d_bests.ensure(sizeof(SswItemBest) * items.size())) return -1;
+	Trace tr;
 	SSW_CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), sizeof(SswItem) * items.size(), cudaMemcpyHostToDevice, stream));
+	tr.lap("  fill: items h2d");
 	t_k.start(stream);
 	int rc = -1;
 	switch (inst) {
@@ -146,7 +149,9 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, b
 	case 10: rc = launch_fill<32, 5>(this, n_items, dir, write_cm, term, P); break;
 	default: break;
 	}
+	tr.lap("  fill: launch");
 	*ms_acc += t_k.stop(stream);
+	tr.lap("  fill: wait");
 	return rc;
 }
 
@@ -194,6 +199,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!e || !name) return -1;
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }
+	if (!strcmp(name, "mode")) { g_fill_mode = value ? 1 : 0; return 0; }
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;
 }
@@ -292,9 +298,11 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 		return x.idx < y.idx;
 	});
 
+	tr.lap("forward: sort");
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);
 	const size_t cm_budget_words = std::max<size_t>((size_t)1 << 22, (free_b + e->d_colmax.cap) / 2 / 4);
+	tr.lap("forward: memgetinfo");
 
 	size_t k = 0;
 	while (k < keys.size()) {
@@ -361,7 +369,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				SswAlnDesc d;
 				d.first_item = first_item; d.n_items = n_chunks; d.half = h; d.ref_len = ref_len; d.read_len = X.read_len;
 				d.word = word;
-				d.limit = word ? 32767 - std::max(max_mat, 0) : 255 - bias;
+				d.limit = word ? 32767 - std::max(max_mat, 0) - 256 : 255 - bias;   /* 256: head-room for the fill kernel's bias */
 				d.mask_len = X.mask_len; d.cm_off = (int64_t)cm_words;
 				descs.push_back(d);
 				desc_aln.push_back(h ? pt.b : pt.a);
@@ -389,6 +397,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			SSW_CUDA_OK(cudaGetLastError());
 		}
 		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		tr.lap("forward: resolve kernel");
 		e->timing.other_launches += 1;
 		std::vector<SswFillResult> res(descs.size());
 		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));

@@ -81,7 +81,17 @@ __device__ static __forceinline__ uint32_t ssw_lds32(ssw_saddr a)
 template <int R>
 static inline size_t ssw_fill_smem_bytes(int n) { return (size_t)SSW_FILL_WARPS * (size_t)(n + 1) * 32 * R * sizeof(uint32_t); }
 
-template <int G, int R, int DIR, bool WRITE_CM, bool TERM>
+/*
+ * MODE 0: every add is a DPX/VIADD instruction (ALU pipe).
+ * MODE 1: "biased" arithmetic.  All of H, E, F, X carry a per-half bias B >= max(gapO, |min(mat)|), which makes
+ *         two of the adds carry-safe as plain 32-bit operations, so they are issued as IMAD on the FMA pipe:
+ *           t  = Hd + s      profile words are stored with the low half's carry pre-compensated in the high half
+ *                            (low half >= 0 after the add for every real score; dead rows use -32768: never a carry)
+ *           Xg = X - gapO    X >= B >= gapO in both halves: never a borrow
+ *         leaving 4.5 ALU-pipe instructions per cell pair (VIMNMX3, 2 x VIADDMNMX, VIMNMX, 1/2 VIMNMX3) instead of 5.5.
+ *         Scores are un-biased when they leave the kernel.
+ */
+template <int G, int R, int DIR, bool WRITE_CM, bool TERM, int MODE>
 __global__ void __launch_bounds__(SSW_FILL_THREADS)
 ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
@@ -110,6 +120,15 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		it.ref_off = SSW_REF_PAD; it.ref_len = 0; it.cend = 0; it.p0 = it.p1 = 0; it.warm = 0; it.term_a = -1; it.cm_off = -1;
 	}
 
+	/* bias of MODE 1 (0 in MODE 0): B >= gapO and B >= -min(mat) */
+	int B = 0;
+	if (MODE == 1) {
+		B = gapO > 1 ? gapO : 1;
+		for (int i = lane; i < n * n; i += 32) B = max(B, -(int)mat[i]);
+#pragma unroll
+		for (int off = 16; off >= 1; off >>= 1) B = max(B, __shfl_xor_sync(FULL, B, off));
+	}
+
 	/* ---- build the packed query profile of this group (qP_byte/qP_word analogue, ssw.c:163-188/:388-410) ---- */
 	{
 		int ca[R], cb[R];
@@ -128,6 +147,8 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 					a = ca[k] >= 0 ? (int)mat[letter * n + ca[k]] : (ca[k] == -1 ? 0 : SSW_NEG16);
 					b = cb[k] >= 0 ? (int)mat[letter * n + cb[k]] : (cb[k] == -1 ? 0 : SSW_NEG16);
 				}
+				/* MODE 1: the 32-bit add Hd + s carries out of the low half exactly when the low score is a real negative one */
+				if (MODE == 1 && a < 0 && a != SSW_NEG16) b -= 1;
 				pl[ssw_prof_slot<R>(k, lane)] = pack2(a, b);
 			}
 		}
@@ -157,11 +178,18 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	asm volatile("" : "+r"(top_keep) : : "memory");     /* opaque 0/1 so that the masking stays a multiply */
 #endif
 
+	const uint32_t Bv = pack2(B, B);                    /* the zero level of every stored quantity */
+	const uint32_t subO = 0u - ((uint32_t)gapO | ((uint32_t)gapO << 16));   /* MODE 1: 32-bit "- gapO" of both halves */
+	const uint32_t top_add = t == 0 ? Bv : 0u;
+	uint32_t one = 1u;
+#ifndef SSW_CPU_EMU
+	asm volatile("" : "+r"(one));                        /* opaque multiplier: keeps the MODE 1 adds as IMAD */
+#endif
 	uint32_t Hd[R], E[R];
 #pragma unroll
-	for (int k = 0; k < R; ++k) { Hd[k] = 0; E[k] = 0; }
-	uint32_t outH = 0, outF = 0, outC = 0;
-	uint32_t best = 0;
+	for (int k = 0; k < R; ++k) { Hd[k] = Bv; E[k] = Bv; }
+	uint32_t outH = Bv, outF = Bv, outC = Bv;
+	uint32_t best = Bv;
 	int bpos0 = 0, bpos1 = 0, brow0 = 0, brow1 = 0;
 	int stopped = 0;
 
@@ -171,9 +199,9 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			/* values crossing the lane boundary */
-			const uint32_t inH = __shfl_up_sync(FULL, outH, 1, G) * top_keep;
-			const uint32_t inF = __shfl_up_sync(FULL, outF, 1, G) * top_keep;
-			const uint32_t inC = __shfl_up_sync(FULL, outC, 1, G) * top_keep;
+			const uint32_t inH = __shfl_up_sync(FULL, outH, 1, G) * top_keep + top_add;
+			const uint32_t inF = __shfl_up_sync(FULL, outF, 1, G) * top_keep + top_add;
+			const uint32_t inC = __shfl_up_sync(FULL, outC, 1, G) * top_keep + top_add;
 
 			/* reference letter of this lane's scan position and its profile rows */
 			int letter = (int)lptr[DIR * j];
@@ -192,11 +220,18 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 			}
 
 			/* R cells of this lane's column */
-			uint32_t F = inF, m = 0, Hn[R];
+			uint32_t F = inF, m = Bv, Hn[R];
 #pragma unroll
 			for (int k = 0; k < R; ++k) {
-				const uint32_t X = __viaddmax_s16x2_relu(Hd[k], s[k], E[k]);
-				const uint32_t Xg = __vadd2(X, negO);
+				uint32_t X, Xg;
+				if (MODE == 1) {
+					const uint32_t tt = Hd[k] * one + s[k];          /* IMAD: carry-compensated packed add */
+					X = __vimax3_s16x2(tt, E[k], Bv);
+					Xg = X * one + subO;                             /* IMAD: borrow-free packed subtract */
+				} else {
+					X = __viaddmax_s16x2_relu(Hd[k], s[k], E[k]);
+					Xg = __vadd2(X, negO);
+				}
 				E[k] = __viaddmax_s16x2(E[k], negE, Xg);
 				Hn[k] = __vmaxs2(X, F);
 				F = __viaddmax_s16x2(F, negE, Xg);
@@ -210,7 +245,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 			outH = Hn[R - 1];
 			outF = F;
 			outC = __vmaxs2(inC, m);
-			cmv[j] = outC;
+			cmv[j] = MODE == 1 ? outC * one + (0u - Bv) : outC;       /* un-biased column maximum (outC >= B: no borrow) */
 
 			/* running best of this lane (strict increase only; rare path) */
 			const uint32_t nb = __vmaxs2(best, m);
@@ -260,7 +295,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	}
 
 	/* ---- reduce the group's lanes to one record per half: max score, then first position, then smallest row ---- */
-	int sc0 = half_of(best, 0), sc1 = half_of(best, 1);
+	int sc0 = half_of(best, 0) - B, sc1 = half_of(best, 1) - B;
 #pragma unroll
 	for (int off = G / 2; off >= 1; off >>= 1) {
 		const int o_sc0 = __shfl_down_sync(FULL, sc0, off, G), o_p0 = __shfl_down_sync(FULL, bpos0, off, G), o_r0 = __shfl_down_sync(FULL, brow0, off, G);
