@@ -107,6 +107,8 @@ struct SswAlnDesc {
 	int32_t limit;      /* byte: 255 - bias (score >= limit overflows); word: 32767 - max(mat) guard */
 	int32_t mask_len;
 	int64_t cm_off;     /* as in SswItem */
+	int32_t scan_all;   /* 1: item records are not column-maximum summaries (strip-pipelined fill): scan every column */
+	int32_t pad_;
 };
 
 /* Output of the resolve kernel (the reference's alignment_end[2], ssw.c:104-108, plus status). */

@@ -16,6 +16,7 @@
 #include <vector>
 #include <string>
 #include <string.h>
+#include <functional>
 
 #include "ssw_common.cuh"
 #include "ssw_host.h"
@@ -46,7 +47,7 @@ static const Inst kInst[] = {
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 static const int kMaxRows = 512;
 
-static int g_fill_mode = 0;        /* fill-kernel arithmetic ("mode" option): 0 all-DPX, 1 biased with IMAD adds */
+static int g_strip_super = SSW_STRIP_SUPER;   /* columns per super-block of the strip kernel ("super" option, tests) */
 static int g_force_inst = -1;      /* experiment knob ("inst" option): use this instance whenever it covers the query */
 static int pick_inst(int lp)
 {
@@ -80,7 +81,7 @@ struct ssw_engine {
 	SswDevBuf d_q, d_r, d_mat;
 
 	/* scratch */
-	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb;
+	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park;
 	int64_t opt_chunk = 0;
 	ssw_engine_timing timing;
 	SswTimer t_total, t_k;
@@ -109,7 +110,7 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, bool write_cm, bool 
 	SswItemBest* bests = e->d_bests.as<SswItemBest>();
 #define SSW_FILL_GO(DIR, CM, TERM)                                                                               \
 	do {                                                                                                         \
-		auto kern = g_fill_mode == 1 ? ssw_fill_kernel<G, R, DIR, CM, TERM, 1> : ssw_fill_kernel<G, R, DIR, CM, TERM, 0>; \
+		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM>;                                                        \
 		if (smem > 48 * 1024)                                                                                    \
 			SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
 		ssw_launch(kern, dim3(grid), dim3(SSW_FILL_THREADS), smem, e->stream, items, n_items, q, r, mat, (int)P.n, \
@@ -186,7 +187,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 {
 	if (!e) return;
 	cudaSetDevice(e->device);
-	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb};
+	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park};
 	for (SswDevBuf* b : bufs) b->release();
 	if (e->stream) cudaStreamDestroy(e->stream);
 	delete e;
@@ -199,7 +200,8 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!e || !name) return -1;
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }
-	if (!strcmp(name, "mode")) { g_fill_mode = value ? 1 : 0; return 0; }
+	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 3) / 4 * 4 : SSW_STRIP_SUPER; return 0; }
+	if (!strcmp(name, "mode")) return 0;      /* retired experiment (biased arithmetic with IMAD adds was slower, profiles/fill_kernel_r1.md) */
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;
 }
@@ -272,6 +274,135 @@ static inline int lp_of(int len, int word) { int g = word ? 8 : 16; return (len 
 
 }  // namespace
 
+
+/* ------------------------------------------------------------------------------------------- */
+/* strip-pipelined fill for queries longer than one strip (ssw_fill_strips_kernel)               */
+/* ------------------------------------------------------------------------------------------- */
+
+struct StripReq {             /* one pair-task (forward) or one alignment (reverse) for the strip kernel */
+	int64_t a, b;             /* indices into alns; b = -1: half B dead */
+	SswQuery qa, qb;
+	int32_t r, cend, p1, term;
+};
+
+/* Launch the strip kernel over `reqs` (all with dir/term alike), resolve, and hand the results back through `sink`. */
+static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vector<StripReq>& reqs, int dir, bool term,
+                      int word, int limit, const std::vector<Aln>& alns, float* ms_acc,
+                      const std::function<void(int64_t aln, const SswFillResult&)>& sink)
+{
+	constexpr int R = SSW_STRIP_R;
+	const int rows_per_strip = 32 * R;
+	const size_t warp_smem = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t);
+	size_t k = 0;
+	/* one launch per distinct strip count (it fixes the CTA shape) */
+	std::vector<size_t> order(reqs.size());
+	for (size_t i = 0; i < reqs.size(); ++i) order[i] = i;
+	auto strips_of = [&](const StripReq& q) { return (std::max(q.qa.lp, q.qb.lp) + rows_per_strip - 1) / rows_per_strip; };
+	std::sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+		const int sx = strips_of(reqs[x]), sy = strips_of(reqs[y]);
+		return sx != sy ? sx < sy : x < y;
+	});
+	while (k < order.size()) {
+		const int n_strips = strips_of(reqs[order[k]]);
+		/* warps per CTA: as many as shared memory allows, preferring a count that divides the strips evenly */
+		int nw_max = (int)std::min<size_t>(SSW_STRIP_MAXW, (200 * 1024) / warp_smem);
+		if (nw_max < 1) { fprintf(stderr, "[libssw-b200] alphabet too large for the strip kernel\n"); return -2; }
+		nw_max = std::min(nw_max, n_strips);
+		int nw = nw_max; double best_eff = 0;
+		for (int w = nw_max; w >= 1; --w) {
+			const double eff = (double)n_strips / (double)(((n_strips + w - 1) / w) * w);
+			if (eff > best_eff + 1e-9) { best_eff = eff; nw = w; }
+		}
+		std::vector<SswStripTask> tasks;
+		std::vector<SswAlnDesc> descs;
+		std::vector<int64_t> desc_aln;
+		size_t cm_words = 0, bnd_words = 0, park_words = 0;
+		int n_best = 0;
+		size_t free_b = 0, total_b = 0;
+		cudaMemGetInfo(&free_b, &total_b);
+		const size_t budget = std::max<size_t>((size_t)256 << 20, (free_b + e->d_bnd.cap + e->d_colmax.cap) / 2);
+		for (; k < order.size() && strips_of(reqs[order[k]]) == n_strips; ++k) {
+			const StripReq& q = reqs[order[k]];
+			SswStripTask T;
+			memset(&T, 0, sizeof(T));
+			T.qa = q.qa; T.qb = q.qb;
+			T.ref_off = e->r_off[q.r]; T.ref_len = e->r_len[q.r]; T.cend = q.cend; T.p1 = q.p1; T.term_a = q.term;
+			T.n_strips = n_strips;
+			T.super = g_strip_super;
+			T.n_super = term ? std::max(1, (q.p1 + T.super - 1) / T.super) : 1;
+			T.bnd_len = ((q.p1 + 3) / 4 * 4) + 2 * SSW_STRIP_BPAD + 64;
+			const size_t need = 4 * (cm_words + bnd_words + park_words + 6 * (size_t)T.bnd_len + (size_t)q.p1 + 8);
+			if (!tasks.empty() && need > budget) break;
+			T.cm_off = dir > 0 ? (int64_t)cm_words : -1;
+			T.bnd_off = (int64_t)bnd_words;
+			T.park_off = (int64_t)park_words;
+			T.first_best = n_best;
+			if (dir > 0) cm_words += ((size_t)q.p1 + 3) / 4 * 4 + 4;
+			bnd_words += 6 * (size_t)T.bnd_len;
+			park_words += (size_t)n_strips * 32 * (2 * R + 3);
+			for (int h = 0; h < (q.b >= 0 ? 2 : 1); ++h) {
+				const Aln& X = alns[h ? q.b : q.a];
+				SswAlnDesc d;
+				memset(&d, 0, sizeof(d));
+				d.first_item = n_best; d.n_items = n_strips * T.n_super; d.half = h;
+				d.ref_len = dir > 0 ? T.ref_len : q.p1;
+				d.read_len = h ? q.qb.len : q.qa.len;
+				d.word = word; d.limit = limit; d.mask_len = X.mask_len; d.cm_off = T.cm_off; d.scan_all = 1;
+				descs.push_back(d);
+				desc_aln.push_back(h ? q.b : q.a);
+			}
+			n_best += n_strips * T.n_super;
+			tasks.push_back(T);
+		}
+		if (e->d_items.ensure(sizeof(SswStripTask) * tasks.size())) return -1;
+		if (e->d_bests.ensure(sizeof(SswItemBest) * (size_t)n_best)) return -1;
+		if (e->d_colmax.ensure(cm_words * 4 + 64)) return -1;
+		if (e->d_bnd.ensure(bnd_words * 4 + 64)) return -1;
+		if (e->d_park.ensure(park_words * 4 + 64)) return -1;
+		SSW_CUDA_OK(cudaMemcpyAsync(e->d_items.p, tasks.data(), sizeof(SswStripTask) * tasks.size(), cudaMemcpyHostToDevice, e->stream));
+		SSW_CUDA_OK(cudaMemsetAsync(e->d_bests.p, 0, sizeof(SswItemBest) * (size_t)n_best, e->stream));
+		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 2);
+		e->t_k.start(e->stream);
+#define SSW_STRIPS_GO(DIR, TERM)                                                                                        \
+		do {                                                                                                            \
+			auto kern = ssw_fill_strips_kernel<SSW_STRIP_R, DIR, TERM>;                                                 \
+			if (smem > 48 * 1024) SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+			ssw_launch(kern, dim3((unsigned)tasks.size()), dim3(nw * 32), smem, e->stream, (const SswStripTask*)e->d_items.as<SswStripTask>(), \
+			           (const int8_t*)e->d_q.as<int8_t>(), (const int8_t*)e->d_r.as<int8_t>(), (const int8_t*)e->d_mat.as<int8_t>(), (int)P.n, \
+			           (int)P.gap_open, (int)P.gap_extend, e->d_colmax.as<uint32_t>(), e->d_bnd.as<uint32_t>(), e->d_park.as<uint32_t>(), \
+			           e->d_bests.as<SswItemBest>());                                                                   \
+		} while (0)
+		if (dir > 0) SSW_STRIPS_GO(1, false); else SSW_STRIPS_GO(-1, true);
+#undef SSW_STRIPS_GO
+		SSW_CUDA_OK(cudaGetLastError());
+		*ms_acc += e->t_k.stop(e->stream);
+		if (dir > 0) e->timing.fill_forward_launches += 1; else e->timing.other_launches += 1;
+
+		if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
+		if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
+		SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
+		e->t_k.start(e->stream);
+		{
+			const int per = SSW_RESOLVE_THREADS / 32;
+			const dim3 grid(((int)descs.size() + per - 1) / per);
+			if (dir > 0)
+				ssw_launch(ssw_resolve_kernel<true>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
+				           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)e->d_colmax.as<uint32_t>(), e->d_res.as<SswFillResult>());
+			else
+				ssw_launch(ssw_resolve_kernel<false>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
+				           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)nullptr, e->d_res.as<SswFillResult>());
+			SSW_CUDA_OK(cudaGetLastError());
+		}
+		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		e->timing.other_launches += 1;
+		std::vector<SswFillResult> res(descs.size());
+		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
+		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+		for (size_t i = 0; i < descs.size(); ++i) sink(desc_aln[i], res[i]);
+	}
+	return 0;
+}
+
 /* Plan and run one forward fill + resolve over the alignments `sel` (indices into alns) with the given semantics. */
 static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>& alns, const std::vector<int64_t>& sel,
                         int word, int bias, int max_mat)
@@ -280,17 +411,47 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	Trace tr;
 	/* order: kernel instance, reference, then query length so that partners are alike */
 	struct Key { int inst; int32_t r; int32_t lp; int64_t idx; };
-	std::vector<Key> keys(sel.size());
+	std::vector<Key> keys;
+	std::vector<Key> long_keys;          /* queries longer than one strip: strip-pipelined kernel */
 	for (size_t i = 0; i < sel.size(); ++i) {
 		const Aln& a = alns[sel[i]];
 		const int lp = lp_of(a.read_len, word);
 		const int inst = pick_inst(lp);
-		if (inst < 0) {
-			fprintf(stderr, "[libssw-b200] query of %d residues exceeds the single-strip limit of %d rows\n", a.read_len, kMaxRows);
-			return -2;
-		}
-		keys[i] = Key{inst, a.r, lp, sel[i]};
+		if (inst < 0) long_keys.push_back(Key{0, a.r, lp, sel[i]});
+		else keys.push_back(Key{inst, a.r, lp, sel[i]});
 	}
+	if (!long_keys.empty()) {
+		std::sort(long_keys.begin(), long_keys.end(), [](const Key& x, const Key& y) {
+			if (x.r != y.r) return x.r < y.r;
+			if (x.lp != y.lp) return x.lp < y.lp;
+			return x.idx < y.idx;
+		});
+		std::vector<StripReq> reqs;
+		for (size_t i = 0; i < long_keys.size();) {
+			StripReq q;
+			memset(&q, 0, sizeof(q));
+			const Aln& A = alns[long_keys[i].idx];
+			q.a = long_keys[i].idx; q.b = -1; q.r = A.r; q.cend = 0; q.p1 = A.ref_len; q.term = -1;
+			q.qa.off = (int32_t)e->q_off[A.q]; q.qa.len = A.read_len; q.qa.lp = long_keys[i].lp; q.qa.rev = 0;
+			++i;
+			if (i < long_keys.size() && long_keys[i].r == A.r) {
+				const Aln& B = alns[long_keys[i].idx];
+				q.b = long_keys[i].idx;
+				q.qb.off = (int32_t)e->q_off[B.q]; q.qb.len = B.read_len; q.qb.lp = long_keys[i].lp; q.qb.rev = 0;
+				++i;
+			}
+			reqs.push_back(q);
+		}
+		const int limit = word ? 32767 - std::max(max_mat, 0) - 256 : 255 - bias;
+		int rc = run_strips(e, P, reqs, +1, false, word, limit, alns, &e->timing.fill_forward_ms,
+		                    [&](int64_t ai, const SswFillResult& r) { alns[ai].fwd = r; alns[ai].word = word; });
+		if (rc) return rc;
+		for (const StripReq& q : reqs) {
+			const int lpmax = std::max(q.qa.lp, q.qb.lp);
+			e->timing.cells_forward += (int64_t)q.p1 * ((lpmax + 32 * SSW_STRIP_R - 1) / (32 * SSW_STRIP_R)) * 32 * SSW_STRIP_R * 2;
+		}
+	}
+	if (keys.empty()) return 0;
 	std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
 		if (x.inst != y.inst) return x.inst < y.inst;
 		if (x.r != y.r) return x.r < y.r;
@@ -367,6 +528,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			for (int h = 0; h < (B ? 2 : 1); ++h) {
 				const Aln& X = h ? *B : A;
 				SswAlnDesc d;
+				memset(&d, 0, sizeof(d));
 				d.first_item = first_item; d.n_items = n_chunks; d.half = h; d.ref_len = ref_len; d.read_len = X.read_len;
 				d.word = word;
 				d.limit = word ? 32767 - std::max(max_mat, 0) - 256 : 255 - bias;   /* 256: head-room for the fill kernel's bias */
@@ -414,12 +576,22 @@ static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 {
 	if (sel.empty()) return 0;
 	struct Key { int inst; int64_t idx; };
-	std::vector<Key> keys(sel.size());
+	std::vector<Key> keys;
+	std::vector<StripReq> long_reqs;
 	for (size_t i = 0; i < sel.size(); ++i) {
 		const Aln& a = alns[sel[i]];
 		const int inst = pick_inst_g32(lp_of(a.fwd.read + 1, a.word));
-		if (inst < 0) return -2;
-		keys[i] = Key{inst, sel[i]};
+		if (inst >= 0) { keys.push_back(Key{inst, sel[i]}); continue; }
+		StripReq q;
+		memset(&q, 0, sizeof(q));
+		q.a = sel[i]; q.b = -1; q.r = a.r; q.cend = a.fwd.ref; q.p1 = a.fwd.ref + 1; q.term = a.fwd.score;
+		q.qa.off = (int32_t)e->q_off[a.q]; q.qa.len = a.fwd.read + 1; q.qa.lp = lp_of(q.qa.len, a.word); q.qa.rev = 1;
+		long_reqs.push_back(q);
+	}
+	if (!long_reqs.empty()) {
+		int rc = run_strips(e, P, long_reqs, -1, true, 1, 0x7fffffff, alns, &e->timing.fill_reverse_ms,
+		                    [&](int64_t ai, const SswFillResult& r) { alns[ai].rev_score = r.score; alns[ai].rev_pos = r.ref; alns[ai].rev_row = r.read; });
+		if (rc) return rc;
 	}
 	std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.inst != y.inst ? x.inst < y.inst : x.idx < y.idx; });
 	size_t k = 0;
@@ -436,6 +608,7 @@ static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			it.ref_off = e->r_off[a.r]; it.ref_len = a.ref_len; it.cend = a.fwd.ref;
 			it.p0 = 0; it.p1 = a.fwd.ref + 1; it.warm = 0; it.term_a = a.fwd.score; it.cm_off = -1;
 			SswAlnDesc d;
+			memset(&d, 0, sizeof(d));
 			d.first_item = (int)items.size(); d.n_items = 1; d.half = 0; d.ref_len = it.p1; d.read_len = it.qa.len;
 			d.word = 1; d.limit = 0x7fffffff; d.mask_len = 0; d.cm_off = -1;
 			items.push_back(it);

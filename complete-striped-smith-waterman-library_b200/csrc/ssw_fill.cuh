@@ -21,6 +21,13 @@
  * the padded reference array (null letters outside [0, refLen) keep the state
  * at exactly zero, so pipeline fill and drain need no predication).
  *
+ * Two kernels share the same cell code:
+ *   ssw_fill_kernel         queries of up to G*R rows: one group per item, items = reference chunks
+ *   ssw_fill_strips_kernel  longer queries: the rows are cut into strips of 32*R rows; the strips of one
+ *                           pair-task run as a software pipeline over the warps of one CTA, each strip
+ *                           consuming the bottom row (H, F, partial column maximum) of the strip above it
+ *                           from a boundary buffer a few columns behind its producer.
+ *
  * Outputs per item: the lexicographic best cell (score, first scan position,
  * smallest row) per half, and -- forward pass -- the column maxima over real
  * and pad rows (the reference's maxColumn[], ssw.c:338/:540) as packed s16x2
@@ -34,6 +41,11 @@
 
 #define SSW_FILL_WARPS 4
 #define SSW_FILL_THREADS (SSW_FILL_WARPS * 32)
+#define SSW_STRIP_R 16                      /* rows per lane of the strip kernel: 512 rows per strip */
+#define SSW_STRIP_MAXW 16                   /* warps per CTA of the strip kernel */
+#define SSW_STRIP_LAG 40                    /* a strip's last lane ends a super-block this many columns before the strip above */
+#define SSW_STRIP_SUPER 4096                /* columns per super-block (granularity of early termination) */
+#define SSW_STRIP_BPAD 32                   /* words in front of every boundary array (scan positions down to -32) */
 
 /* word offset of row k of lane `lane` inside one letter's profile block (32*R words):
  * R = 4a + rem; the first 4a rows are a uint4 segments [seg][lane], the tail is [lane][rem]. */
@@ -77,21 +89,136 @@ __device__ static __forceinline__ uint32_t ssw_lds32(ssw_saddr a)
 }
 #endif
 
-/* shared-memory bytes the fill kernel needs for an alphabet of n letters */
+/* shared-memory bytes for an alphabet of n letters */
 template <int R>
-static inline size_t ssw_fill_smem_bytes(int n) { return (size_t)SSW_FILL_WARPS * (size_t)(n + 1) * 32 * R * sizeof(uint32_t); }
+static inline size_t ssw_fill_smem_bytes(int n, int warps = SSW_FILL_WARPS) { return (size_t)warps * (size_t)(n + 1) * 32 * R * sizeof(uint32_t); }
 
-/*
- * MODE 0: every add is a DPX/VIADD instruction (ALU pipe).
- * MODE 1: "biased" arithmetic.  All of H, E, F, X carry a per-half bias B >= max(gapO, |min(mat)|), which makes
- *         two of the adds carry-safe as plain 32-bit operations, so they are issued as IMAD on the FMA pipe:
- *           t  = Hd + s      profile words are stored with the low half's carry pre-compensated in the high half
- *                            (low half >= 0 after the add for every real score; dead rows use -32768: never a carry)
- *           Xg = X - gapO    X >= B >= gapO in both halves: never a borrow
- *         leaving 4.5 ALU-pipe instructions per cell pair (VIMNMX3, 2 x VIADDMNMX, VIMNMX, 1/2 VIMNMX3) instead of 5.5.
- *         Scores are un-biased when they leave the kernel.
- */
-template <int G, int R, int DIR, bool WRITE_CM, bool TERM, int MODE>
+/* ---------------------------------------------------------------------------------------------------------- */
+/* shared device code                                                                                          */
+/* ---------------------------------------------------------------------------------------------------------- */
+
+/* Build the packed profile rows [row0, row0 + R) of this lane for both queries into `prof`
+ * (qP_byte / qP_word analogue, ssw.c:163-188 / :388-410): real rows score mat[letter][code], pad rows 0,
+ * rows beyond the query's padded length and the null letter n score -32768 (dead: H stays 0). */
+template <int R>
+__device__ static __forceinline__ void ssw_build_profile(uint32_t* prof, int lane, int row0, const SswQuery& qa, const SswQuery& qb,
+                                                        const int8_t* __restrict__ qcodes, const int8_t* __restrict__ mat, int n)
+{
+	int ca[R], cb[R];
+#pragma unroll
+	for (int k = 0; k < R; ++k) {
+		const int row = row0 + k;
+		ca[k] = row < qa.len ? (int)qcodes[qa.off + (qa.rev ? qa.len - 1 - row : row)] : (row < qa.lp ? -1 : -2);
+		cb[k] = row < qb.len ? (int)qcodes[qb.off + (qb.rev ? qb.len - 1 - row : row)] : (row < qb.lp ? -1 : -2);
+	}
+	for (int letter = 0; letter <= n; ++letter) {
+		uint32_t* pl = prof + letter * (32 * R);
+#pragma unroll
+		for (int k = 0; k < R; ++k) {
+			int a = SSW_NEG16, b = SSW_NEG16;
+			if (letter < n) {
+				a = ca[k] >= 0 ? (int)mat[letter * n + ca[k]] : (ca[k] == -1 ? 0 : SSW_NEG16);
+				b = cb[k] >= 0 ? (int)mat[letter * n + cb[k]] : (cb[k] == -1 ? 0 : SSW_NEG16);
+			}
+			pl[ssw_prof_slot<R>(k, lane)] = pack2(a, b);
+		}
+	}
+}
+
+/* Profile rows of this lane for one reference letter. */
+template <int R>
+__device__ static __forceinline__ void ssw_load_scores(uint32_t (&s)[R], ssw_saddr pbase, ssw_saddr ptail, int letter)
+{
+	constexpr int A4 = R / 4, REM = R % 4;
+	const ssw_saddr pl = ssw_sadd(pbase, letter * (32 * R));
+#pragma unroll
+	for (int q = 0; q < A4; ++q) {
+		const uint4 v = ssw_lds128(ssw_sadd(pl, q * 128));
+		s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+	}
+	if (REM == 1) s[4 * A4] = ssw_lds32(ssw_sadd(ptail, letter * (32 * R)));
+	if (REM == 2) {
+		const uint2 v = ssw_lds64(ssw_sadd(ptail, letter * (32 * R)));
+		s[4 * A4] = v.x; s[4 * A4 + 1] = v.y;
+	}
+}
+
+/* The R cells of one lane in one column: 5 DPX/ALU instructions per cell pair + 1/2 for the column maximum.
+ * In: Hd (H of the previous column, shifted down one row), E, scores, and (inH, inF) from the lane above.
+ * Out: Hn (H of this column), updated E and Hd, outH/outF for the lane below, m = max over the lane's rows. */
+template <int R>
+__device__ static __forceinline__ void ssw_cells(uint32_t (&Hd)[R], uint32_t (&E)[R], const uint32_t (&s)[R], uint32_t (&Hn)[R],
+                                                uint32_t inH, uint32_t inF, uint32_t negO, uint32_t negE,
+                                                uint32_t& outH, uint32_t& outF, uint32_t& m)
+{
+	uint32_t F = inF;
+#pragma unroll
+	for (int k = 0; k < R; ++k) {
+		const uint32_t X = __viaddmax_s16x2_relu(Hd[k], s[k], E[k]);
+		const uint32_t Xg = __vadd2(X, negO);
+		E[k] = __viaddmax_s16x2(E[k], negE, Xg);
+		Hn[k] = __vmaxs2(X, F);
+		F = __viaddmax_s16x2(F, negE, Xg);
+	}
+	m = 0;
+#pragma unroll
+	for (int k = 0; k + 1 < R; k += 2) m = __vimax3_s16x2(m, Hn[k], Hn[k + 1]);
+	if (R & 1) m = __vmaxs2(m, Hn[R - 1]);
+	Hd[0] = inH;
+#pragma unroll
+	for (int k = 1; k < R; ++k) Hd[k] = Hn[k - 1];
+	outH = Hn[R - 1];
+	outF = F;
+}
+
+/* Running best of one lane: on a strict increase of either half record the scan position and the smallest row. */
+struct SswLaneBest {
+	uint32_t best;
+	int pos0, pos1, row0, row1;
+};
+
+template <int R>
+__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1, int row_base)
+{
+#ifndef SSW_CPU_EMU
+	asm volatile("" : "+r"(sp));                /* keep the range test inside this rare path */
+#endif
+	if (sp >= p0 && sp < p1) {
+		if (half_of(nb, 0) > half_of(lb.best, 0)) {
+			lb.pos0 = sp;
+#pragma unroll
+			for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 0) == half_of(nb, 0)) lb.row0 = row_base + k;
+		}
+		if (half_of(nb, 1) > half_of(lb.best, 1)) {
+			lb.pos1 = sp;
+#pragma unroll
+			for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 1) == half_of(nb, 1)) lb.row1 = row_base + k;
+		}
+		lb.best = nb;
+	}
+}
+
+/* Reduce the lanes of a group to one record per half: max score, then first position, then smallest row. */
+template <int G>
+__device__ static __forceinline__ void ssw_reduce_best(const SswLaneBest& lb, int& sc0, int& p0, int& r0, int& sc1, int& p1, int& r1)
+{
+	constexpr unsigned FULL = 0xffffffffu;
+	sc0 = half_of(lb.best, 0); sc1 = half_of(lb.best, 1);
+	p0 = lb.pos0; p1 = lb.pos1; r0 = lb.row0; r1 = lb.row1;
+#pragma unroll
+	for (int off = G / 2; off >= 1; off >>= 1) {
+		const int o_sc0 = __shfl_down_sync(FULL, sc0, off, G), o_p0 = __shfl_down_sync(FULL, p0, off, G), o_r0 = __shfl_down_sync(FULL, r0, off, G);
+		const int o_sc1 = __shfl_down_sync(FULL, sc1, off, G), o_p1 = __shfl_down_sync(FULL, p1, off, G), o_r1 = __shfl_down_sync(FULL, r1, off, G);
+		if (o_sc0 > sc0 || (o_sc0 == sc0 && (o_p0 < p0 || (o_p0 == p0 && o_r0 < r0)))) { sc0 = o_sc0; p0 = o_p0; r0 = o_r0; }
+		if (o_sc1 > sc1 || (o_sc1 == sc1 && (o_p1 < p1 || (o_p1 == p1 && o_r1 < r1)))) { sc1 = o_sc1; p1 = o_p1; r1 = o_r1; }
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* single-strip kernel                                                                                          */
+/* ---------------------------------------------------------------------------------------------------------- */
+
+template <int G, int R, int DIR, bool WRITE_CM, bool TERM>
 __global__ void __launch_bounds__(SSW_FILL_THREADS)
 ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
@@ -109,7 +236,6 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int g = lane / G, t = lane % G;
 	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
-	const int letter_stride = 32 * R;
 
 	const int item_idx = ((int)blockIdx.x * SSW_FILL_WARPS + warp) * GPW + g;
 	const bool live = item_idx < n_items;
@@ -120,39 +246,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		it.ref_off = SSW_REF_PAD; it.ref_len = 0; it.cend = 0; it.p0 = it.p1 = 0; it.warm = 0; it.term_a = -1; it.cm_off = -1;
 	}
 
-	/* bias of MODE 1 (0 in MODE 0): B >= gapO and B >= -min(mat) */
-	int B = 0;
-	if (MODE == 1) {
-		B = gapO > 1 ? gapO : 1;
-		for (int i = lane; i < n * n; i += 32) B = max(B, -(int)mat[i]);
-#pragma unroll
-		for (int off = 16; off >= 1; off >>= 1) B = max(B, __shfl_xor_sync(FULL, B, off));
-	}
-
-	/* ---- build the packed query profile of this group (qP_byte/qP_word analogue, ssw.c:163-188/:388-410) ---- */
-	{
-		int ca[R], cb[R];
-#pragma unroll
-		for (int k = 0; k < R; ++k) {
-			const int row = t * R + k;
-			ca[k] = row < it.qa.len ? (int)qcodes[it.qa.off + (it.qa.rev ? it.qa.len - 1 - row : row)] : (row < it.qa.lp ? -1 : -2);
-			cb[k] = row < it.qb.len ? (int)qcodes[it.qb.off + (it.qb.rev ? it.qb.len - 1 - row : row)] : (row < it.qb.lp ? -1 : -2);
-		}
-		for (int letter = 0; letter <= n; ++letter) {
-			uint32_t* pl = prof + letter * letter_stride;
-#pragma unroll
-			for (int k = 0; k < R; ++k) {
-				int a = SSW_NEG16, b = SSW_NEG16;
-				if (letter < n) {
-					a = ca[k] >= 0 ? (int)mat[letter * n + ca[k]] : (ca[k] == -1 ? 0 : SSW_NEG16);
-					b = cb[k] >= 0 ? (int)mat[letter * n + cb[k]] : (cb[k] == -1 ? 0 : SSW_NEG16);
-				}
-				/* MODE 1: the 32-bit add Hd + s carries out of the low half exactly when the low score is a real negative one */
-				if (MODE == 1 && a < 0 && a != SSW_NEG16) b -= 1;
-				pl[ssw_prof_slot<R>(k, lane)] = pack2(a, b);
-			}
-		}
-	}
+	ssw_build_profile<R>(prof, lane, t * R, it.qa, it.qb, qcodes, mat, n);
 	__syncwarp();
 
 	/* ---- sweep ---- */
@@ -178,20 +272,12 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	asm volatile("" : "+r"(top_keep) : : "memory");     /* opaque 0/1 so that the masking stays a multiply */
 #endif
 
-	const uint32_t Bv = pack2(B, B);                    /* the zero level of every stored quantity */
-	const uint32_t subO = 0u - ((uint32_t)gapO | ((uint32_t)gapO << 16));   /* MODE 1: 32-bit "- gapO" of both halves */
-	const uint32_t top_add = t == 0 ? Bv : 0u;
-	uint32_t one = 1u;
-#ifndef SSW_CPU_EMU
-	asm volatile("" : "+r"(one));                        /* opaque multiplier: keeps the MODE 1 adds as IMAD */
-#endif
 	uint32_t Hd[R], E[R];
 #pragma unroll
-	for (int k = 0; k < R; ++k) { Hd[k] = Bv; E[k] = Bv; }
-	uint32_t outH = Bv, outF = Bv, outC = Bv;
-	uint32_t best = Bv;
-	int bpos0 = 0, bpos1 = 0, brow0 = 0, brow1 = 0;
-	int stopped = 0;
+	for (int k = 0; k < R; ++k) { Hd[k] = 0; E[k] = 0; }
+	uint32_t outH = 0, outF = 0, outC = 0;
+	SswLaneBest lb;
+	lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
 
 	for (int body = 0; body < n_body; ++body) {
 		uint32_t cmv[4];
@@ -199,75 +285,22 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			/* values crossing the lane boundary */
-			const uint32_t inH = __shfl_up_sync(FULL, outH, 1, G) * top_keep + top_add;
-			const uint32_t inF = __shfl_up_sync(FULL, outF, 1, G) * top_keep + top_add;
-			const uint32_t inC = __shfl_up_sync(FULL, outC, 1, G) * top_keep + top_add;
+			const uint32_t inH = __shfl_up_sync(FULL, outH, 1, G) * top_keep;
+			const uint32_t inF = __shfl_up_sync(FULL, outF, 1, G) * top_keep;
+			const uint32_t inC = __shfl_up_sync(FULL, outC, 1, G) * top_keep;
 
 			/* reference letter of this lane's scan position and its profile rows */
 			int letter = (int)lptr[DIR * j];
 			if (DIR < 0) { if (sp0 + j < 0) letter = n; }
-			const ssw_saddr pl = ssw_sadd(pbase, letter * letter_stride);
-			uint32_t s[R];
-#pragma unroll
-			for (int q = 0; q < A4; ++q) {
-				const uint4 v = ssw_lds128(ssw_sadd(pl, q * 128));
-				s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
-			}
-			if (REM == 1) s[4 * A4] = ssw_lds32(ssw_sadd(ptail, letter * letter_stride));
-			if (REM == 2) {
-				const uint2 v = ssw_lds64(ssw_sadd(ptail, letter * letter_stride));
-				s[4 * A4] = v.x; s[4 * A4 + 1] = v.y;
-			}
-
-			/* R cells of this lane's column */
-			uint32_t F = inF, m = Bv, Hn[R];
-#pragma unroll
-			for (int k = 0; k < R; ++k) {
-				uint32_t X, Xg;
-				if (MODE == 1) {
-					const uint32_t tt = Hd[k] * one + s[k];          /* IMAD: carry-compensated packed add */
-					X = __vimax3_s16x2(tt, E[k], Bv);
-					Xg = X * one + subO;                             /* IMAD: borrow-free packed subtract */
-				} else {
-					X = __viaddmax_s16x2_relu(Hd[k], s[k], E[k]);
-					Xg = __vadd2(X, negO);
-				}
-				E[k] = __viaddmax_s16x2(E[k], negE, Xg);
-				Hn[k] = __vmaxs2(X, F);
-				F = __viaddmax_s16x2(F, negE, Xg);
-			}
-#pragma unroll
-			for (int k = 0; k + 1 < R; k += 2) m = __vimax3_s16x2(m, Hn[k], Hn[k + 1]);
-			if (R & 1) m = __vmaxs2(m, Hn[R - 1]);
-			Hd[0] = inH;
-#pragma unroll
-			for (int k = 1; k < R; ++k) Hd[k] = Hn[k - 1];
-			outH = Hn[R - 1];
-			outF = F;
+			uint32_t s[R], Hn[R], m;
+			ssw_load_scores<R>(s, pbase, ptail, letter);
+			ssw_cells<R>(Hd, E, s, Hn, inH, inF, negO, negE, outH, outF, m);
 			outC = __vmaxs2(inC, m);
-			cmv[j] = MODE == 1 ? outC * one + (0u - Bv) : outC;       /* un-biased column maximum (outC >= B: no borrow) */
+			cmv[j] = outC;
 
 			/* running best of this lane (strict increase only; rare path) */
-			const uint32_t nb = __vmaxs2(best, m);
-			if (nb != best && maybe_counted) {
-				int sp = sp0 + j;
-#ifndef SSW_CPU_EMU
-				asm volatile("" : "+r"(sp));                /* keep the range test inside the rare path */
-#endif
-				if (sp >= it.p0 && sp < it.p1) {
-					if (half_of(nb, 0) > half_of(best, 0)) {
-						bpos0 = sp;
-#pragma unroll
-						for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 0) == half_of(nb, 0)) brow0 = t * R + k;
-					}
-					if (half_of(nb, 1) > half_of(best, 1)) {
-						bpos1 = sp;
-#pragma unroll
-						for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 1) == half_of(nb, 1)) brow1 = t * R + k;
-					}
-					best = nb;
-				}
-			}
+			const uint32_t nb = __vmaxs2(lb.best, m);
+			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, nb, Hn, sp0 + j, it.p0, it.p1, t * R);
 		}
 
 		if (WRITE_CM) {
@@ -282,7 +315,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 				for (int j = 0; j < 4; ++j)
 					if (sL + j >= it.p0 && sL + j < it.p1 && half_of(cmv[j], 0) == it.term_a) hit = 1;
 			}
-			if (__any_sync(FULL, hit)) { stopped = 1; break; }
+			if (__any_sync(FULL, hit)) break;
 		}
 
 		sL += 4;
@@ -294,21 +327,217 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		}
 	}
 
-	/* ---- reduce the group's lanes to one record per half: max score, then first position, then smallest row ---- */
-	int sc0 = half_of(best, 0) - B, sc1 = half_of(best, 1) - B;
-#pragma unroll
-	for (int off = G / 2; off >= 1; off >>= 1) {
-		const int o_sc0 = __shfl_down_sync(FULL, sc0, off, G), o_p0 = __shfl_down_sync(FULL, bpos0, off, G), o_r0 = __shfl_down_sync(FULL, brow0, off, G);
-		const int o_sc1 = __shfl_down_sync(FULL, sc1, off, G), o_p1 = __shfl_down_sync(FULL, bpos1, off, G), o_r1 = __shfl_down_sync(FULL, brow1, off, G);
-		if (o_sc0 > sc0 || (o_sc0 == sc0 && (o_p0 < bpos0 || (o_p0 == bpos0 && o_r0 < brow0)))) { sc0 = o_sc0; bpos0 = o_p0; brow0 = o_r0; }
-		if (o_sc1 > sc1 || (o_sc1 == sc1 && (o_p1 < bpos1 || (o_p1 == bpos1 && o_r1 < brow1)))) { sc1 = o_sc1; bpos1 = o_p1; brow1 = o_r1; }
-	}
+	int sc0, bp0, br0, sc1, bp1, br1;
+	ssw_reduce_best<G>(lb, sc0, bp0, br0, sc1, bp1, br1);
 	if (live && t == 0) {
 		SswItemBest b;
-		b.score[0] = sc0; b.pos[0] = bpos0; b.row[0] = brow0;
-		b.score[1] = sc1; b.pos[1] = bpos1; b.row[1] = brow1;
+		b.score[0] = sc0; b.pos[0] = bp0; b.row[0] = br0;
+		b.score[1] = sc1; b.pos[1] = bp1; b.row[1] = br1;
 		b.p0 = it.p0; b.p1 = it.p1;
 		bests[item_idx] = b;
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------------------- */
+/* strip-pipelined kernel for queries longer than one strip                                                     */
+/* ---------------------------------------------------------------------------------------------------------- */
+
+/*
+ * One CTA per pair-task, NW = blockDim.x/32 warps.  Strip s = rows [s*32R, (s+1)*32R) is processed by warp
+ * s % NW.  Work is cut into n_super super-blocks of SSW_STRIP_SUPER columns; inside a super-block the strips
+ * run as a pipeline: for every column strip s takes the bottom row of strip s-1 (H, F, partial column maximum)
+ * from that strip's boundary arrays and publishes its own.  prog[s] (shared memory) is the number of columns
+ * strip s has published.  Strip s's last lane ends a super-block SSW_STRIP_LAG*s columns before the block's
+ * end, so everything it needs from strip s-1 (36 columns ahead of its last lane) has been published; between
+ * super-blocks a strip's lane registers are parked in global memory.  Tasks depend only on lexicographically
+ * smaller (super-block, strip) tasks and every warp runs its tasks in that order, so the spin-waits cannot
+ * dead-lock.  The reverse pass raises a CTA-wide stop flag when the last strip meets the terminate score;
+ * at most about one super-block is computed in vain.  Every (strip, super-block) writes its own
+ * SswItemBest record (zeroed by the host beforehand); the resolve kernel reduces them.
+ */
+struct SswStripTask {
+	SswQuery qa, qb;
+	int64_t ref_off;
+	int32_t ref_len, cend;
+	int32_t p1;            /* scan range [0, p1) */
+	int32_t term_a;        /* reverse pass: terminate score, else -1 */
+	int32_t n_strips, n_super;
+	int64_t cm_off;        /* column maxima written by the last strip (forward pass), -1: none */
+	int64_t bnd_off;       /* boundary arrays: 2 (strip parity) x 3 (H, F, C) x bnd_len words */
+	int32_t bnd_len;       /* words per boundary array: multiple of 4, >= p1 + 2*SSW_STRIP_BPAD + 8 */
+	int32_t first_best;    /* record of (strip s, super-block b) = first_best + s * n_super + b */
+	int64_t park_off;      /* parked lane registers: n_strips x 32 lanes x (2R + 3) words */
+	int32_t super;         /* columns per super-block (multiple of 4) */
+	int32_t pad_;
+};
+
+#ifdef SSW_CPU_EMU
+template <class T> __device__ static __forceinline__ T ssw_ldcg(const T* p) { return *p; }
+#define SSW_SPIN_PAUSE() cuemu::yield_now()          /* cooperative fibers: let the producer run */
+#else
+template <class T> __device__ static __forceinline__ T ssw_ldcg(const T* p) { return __ldcg(p); }
+#define SSW_SPIN_PAUSE() __nanosleep(64)
+#endif
+
+template <int R, int DIR, bool TERM>
+__global__ void __launch_bounds__(SSW_STRIP_MAXW * 32)
+ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
+                       const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
+                       const int8_t* __restrict__ mat, int n, int gapO, int gapE,
+                       uint32_t* __restrict__ colmax, uint32_t* bnd, uint32_t* park,
+                       SswItemBest* __restrict__ bests)
+{
+	constexpr int A4 = R / 4, REM = R % 4;
+	constexpr unsigned FULL = 0xffffffffu;
+	constexpr int PARK = 2 * R + 3;
+	static_assert(R % 4 != 3, "rows per lane");
+
+	SSW_DYN_SMEM(uint32_t, smem);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+	const SswStripTask T = tasks[blockIdx.x];
+	/* shared memory: NW profiles, then prog[n_strips], then the stop flag */
+	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
+	volatile int* prog = reinterpret_cast<volatile int*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R);
+	volatile int* stop = prog + T.n_strips;
+	for (int i = threadIdx.x; i < T.n_strips; i += blockDim.x) prog[i] = -0x40000000;
+	if (threadIdx.x == 0) *stop = 0;
+	__syncthreads();
+
+	const uint8_t* rp = reinterpret_cast<const uint8_t*>(refs) + T.ref_off;
+	const uint32_t negO = pack2(-gapO, -gapO), negE = pack2(-gapE, -gapE);
+	const int col_hi = T.ref_len + SSW_REF_PAD - 4, col_lo = -SSW_REF_PAD + 3;
+	const ssw_saddr pbase = ssw_sadd(ssw_sbase(prof), lane * 4);
+	const ssw_saddr ptail = ssw_sadd(ssw_sbase(prof), A4 * 128 + lane * REM);
+	const int start = -32;                               /* first last-lane position: lane 0 starts at -1 */
+	const int end = (T.p1 + 3) & ~3;                     /* last-lane positions run over [start, end) */
+
+	for (int sb = 0; sb < T.n_super; ++sb) {
+		for (int s = warp; s < T.n_strips; s += NW) {
+			/* last-lane range [lo, hi) of this strip in this super-block */
+			const int lag = s * SSW_STRIP_LAG;
+			int lo = sb == 0 ? start : max(start, min(end, sb * T.super - lag));
+			int hi = sb == T.n_super - 1 ? end : max(start, min(end, (sb + 1) * T.super - lag));
+			if (hi <= lo) continue;
+			if (TERM) { int st = lane == 0 ? *stop : 0; st = __shfl_sync(FULL, st, 0); if (st) break; }
+
+			ssw_build_profile<R>(prof, lane, s * 32 * R + lane * R, T.qa, T.qb, qcodes, mat, n);
+			__syncwarp();
+
+			/* lane registers: fresh at the strip's first column, else un-parked */
+			uint32_t Hd[R], E[R], outH, outF, outC;
+			uint32_t* pk = park + T.park_off + ((size_t)s * 32 + lane) * PARK;
+			if (lo == start) {
+#pragma unroll
+				for (int k = 0; k < R; ++k) { Hd[k] = 0; E[k] = 0; }
+				outH = outF = outC = 0;
+			} else {
+#pragma unroll
+				for (int k = 0; k < R; ++k) { Hd[k] = pk[k]; E[k] = pk[R + k]; }
+				outH = pk[2 * R]; outF = pk[2 * R + 1]; outC = pk[2 * R + 2];
+			}
+			SswLaneBest lb;
+			lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
+
+			const uint32_t* bin = bnd + T.bnd_off + (size_t)((s + 1) & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;   /* written by strip s-1 */
+			uint32_t* bout = bnd + T.bnd_off + (size_t)(s & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;
+			int sL = lo;
+			int sp0 = sL + (31 - lane);
+			int col = DIR > 0 ? sp0 : T.cend - sp0;
+			if (DIR > 0) col = min(col, col_hi); else col = max(col, col_lo);
+			const uint8_t* lptr = rp + col;
+			bool stopped = false;
+
+			/* lane 0 is at scan position sL+31 .. sL+34 during a body: the last word of the aligned group at
+			 * sL+28 (carried from the previous body) and the first three of the group at sL+32 */
+			uint32_t cH = 0, cF = 0, cC = 0;
+			if (s > 0 && lane == 0 && sL + 28 >= 0) {
+				cH = ssw_ldcg(bin + sL + 31); cF = ssw_ldcg(bin + T.bnd_len + sL + 31); cC = ssw_ldcg(bin + 2 * T.bnd_len + sL + 31);
+			}
+
+			for (; sL < hi; sL += 4) {
+				uint4 gH = make_uint4(0, 0, 0, 0), gF = gH, gC = gH;
+				int st = 0;                                  /* the stop flag as lane 0 saw it (warp-uniform after the broadcast) */
+				if (lane == 0) {
+					if (s > 0) {
+						const int need = min(sL + 36, end);
+						while (prog[s - 1] < need && !(st = *stop)) { SSW_SPIN_PAUSE(); }
+						__threadfence_block();
+						gH = ssw_ldcg(reinterpret_cast<const uint4*>(bin + sL + 32));
+						gF = ssw_ldcg(reinterpret_cast<const uint4*>(bin + T.bnd_len + sL + 32));
+						gC = ssw_ldcg(reinterpret_cast<const uint4*>(bin + 2 * T.bnd_len + sL + 32));
+					}
+					if (TERM) st = *stop;
+				}
+				st = __shfl_sync(FULL, st, 0);
+				if (TERM) { if (st) { stopped = true; break; } }
+				const uint32_t bHv[4] = {cH, gH.x, gH.y, gH.z}, bFv[4] = {cF, gF.x, gF.y, gF.z}, bCv[4] = {cC, gC.x, gC.y, gC.z};
+				cH = gH.w; cF = gF.w; cC = gC.w;
+				uint32_t cmv[4], hv[4], fv[4];
+				const bool maybe_counted = sp0 + 3 >= 0 && sp0 < T.p1;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					uint32_t inH = __shfl_up_sync(FULL, outH, 1);
+					uint32_t inF = __shfl_up_sync(FULL, outF, 1);
+					uint32_t inC = __shfl_up_sync(FULL, outC, 1);
+					if (lane == 0) { inH = bHv[j]; inF = bFv[j]; inC = bCv[j]; }
+					int letter = (int)lptr[DIR * j];
+					if (sp0 + j < 0) letter = n;                    /* before the scan start (reverse: right of cend) */
+					uint32_t sc[R], Hn[R], m;
+					ssw_load_scores<R>(sc, pbase, ptail, letter);
+					ssw_cells<R>(Hd, E, sc, Hn, inH, inF, negO, negE, outH, outF, m);
+					outC = __vmaxs2(inC, m);
+					cmv[j] = outC; hv[j] = outH; fv[j] = outF;
+					const uint32_t nb = __vmaxs2(lb.best, m);
+					if (nb != lb.best && maybe_counted) ssw_track<R>(lb, nb, Hn, sp0 + j, 0, T.p1, s * 32 * R + lane * R);
+				}
+				/* the last lane publishes the strip's bottom row (the last strip: the column maxima) */
+				if (lane == 31 && sL >= 0) {
+					if (s + 1 < T.n_strips) {
+						*reinterpret_cast<uint4*>(bout + sL) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+						*reinterpret_cast<uint4*>(bout + T.bnd_len + sL) = make_uint4(fv[0], fv[1], fv[2], fv[3]);
+						*reinterpret_cast<uint4*>(bout + 2 * T.bnd_len + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
+						__threadfence_block();
+						prog[s] = sL + 4;
+					} else if (T.cm_off >= 0 && sL < T.p1) {
+						*reinterpret_cast<uint4*>(colmax + T.cm_off + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
+					}
+				}
+				if (TERM && s + 1 == T.n_strips) {
+					int hit = 0;
+					if (lane == 31 && T.term_a >= 0) {
+#pragma unroll
+						for (int j = 0; j < 4; ++j)
+							if (sL + j >= 0 && sL + j < T.p1 && half_of(cmv[j], 0) == T.term_a) hit = 1;
+					}
+					if (__any_sync(FULL, hit)) { if (lane == 0) *stop = 1; stopped = true; break; }
+				}
+				sp0 += 4;
+				{
+					const int ncol = DIR > 0 ? min(col + 4, col_hi) : max(col - 4, col_lo);
+					lptr += ncol - col;
+					col = ncol;
+				}
+			}
+
+			/* park the lane registers for the strip's next super-block */
+			if (!stopped && hi < end) {
+#pragma unroll
+				for (int k = 0; k < R; ++k) { pk[k] = Hd[k]; pk[R + k] = E[k]; }
+				pk[2 * R] = outH; pk[2 * R + 1] = outF; pk[2 * R + 2] = outC;
+			}
+			int sc0, bp0, br0, sc1, bp1, br1;
+			ssw_reduce_best<32>(lb, sc0, bp0, br0, sc1, bp1, br1);
+			if (lane == 0) {
+				SswItemBest b;
+				b.score[0] = sc0; b.pos[0] = bp0; b.row[0] = br0;
+				b.score[1] = sc1; b.pos[1] = bp1; b.row[1] = br1;
+				b.p0 = 0; b.p1 = T.p1;
+				bests[T.first_best + s * T.n_super + sb] = b;
+			}
+			__syncwarp();
+			if (stopped) break;
+		}
+		if (TERM) { int st = lane == 0 ? *stop : 0; st = __shfl_sync(FULL, st, 0); if (st) break; }
 	}
 }
 

@@ -38,18 +38,20 @@ ssw_resolve_kernel(const SswAlnDesc* __restrict__ alns, int n_aln,
 	const SswAlnDesc d = alns[idx];
 	const int h = d.half;
 
-	/* best cell over the alignment's items: max score, then earliest item */
-	int sc = 0, it_i = 0x7fffffff, pos = 0, row = 0;
+	/* best cell over the alignment's records: max score, then first scan position, then smallest row */
+	int sc = 0, pos = 0x7fffffff, row = 0x7fffffff;
 	for (int k = lane; k < d.n_items; k += 32) {
 		const SswItemBest b = bests[d.first_item + k];
-		if (b.score[h] > sc) { sc = b.score[h]; it_i = k; pos = b.pos[h]; row = b.row[h]; }
+		const int s = b.score[h], p = b.pos[h], rr = b.row[h];
+		if (s > 0 && (s > sc || (s == sc && (p < pos || (p == pos && rr < row))))) { sc = s; pos = p; row = rr; }
 	}
 #pragma unroll
 	for (int off = 16; off >= 1; off >>= 1) {
-		const int o_sc = __shfl_xor_sync(FULL, sc, off), o_it = __shfl_xor_sync(FULL, it_i, off);
+		const int o_sc = __shfl_xor_sync(FULL, sc, off);
 		const int o_pos = __shfl_xor_sync(FULL, pos, off), o_row = __shfl_xor_sync(FULL, row, off);
-		if (o_sc > sc || (o_sc == sc && o_it < it_i)) { sc = o_sc; it_i = o_it; pos = o_pos; row = o_row; }
+		if (o_sc > sc || (o_sc == sc && (o_pos < pos || (o_pos == pos && o_row < row)))) { sc = o_sc; pos = o_pos; row = o_row; }
 	}
+	if (sc == 0) { pos = 0; row = 0; }
 
 	SswFillResult r;
 	r.score = sc; r.ref = pos; r.read = row < d.read_len - 1 ? row : d.read_len - 1;
@@ -63,6 +65,14 @@ ssw_resolve_kernel(const SswAlnDesc* __restrict__ alns, int n_aln,
 		const int e2 = min(pos + d.mask_len, d.ref_len) + (d.word ? 0 : 1);
 		const uint32_t* cm = colmax + d.cm_off;
 		int v2 = 0, i2 = 0;
+		if (d.scan_all) {
+			for (int c = lane; c < d.ref_len; c += 32) {
+				if (c < e1 || c >= e2) {
+					const int v = half_of(cm[c], h);
+					if (ssw_second_better(v, c, v2, i2)) { v2 = v; i2 = c; }
+				}
+			}
+		} else
 		for (int k0 = 0; k0 < d.n_items; k0 += 32) {
 			const int k = k0 + lane;
 			bool straddles = false;

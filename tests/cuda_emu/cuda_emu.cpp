@@ -9,6 +9,7 @@ namespace cuemu {
 
 Block* g_block = nullptr;
 static const size_t kStack = 256 * 1024;
+static long g_deadlock_spins = getenv("CUEMU_DEADLOCK_SPINS") ? atol(getenv("CUEMU_DEADLOCK_SPINS")) : 200000000L;
 
 static void fiber_entry() {
 	Block* b = g_block;
@@ -84,7 +85,12 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
 				swapcontext(&blk.sched, &f.ctx);
 				if (f.done) { --live; ++progressed; }
 			}
-			if (!progressed && ++spins > 200000000L) { fprintf(stderr, "cuda_emu: block appears deadlocked\n"); abort(); }
+			if (!progressed && ++spins > g_deadlock_spins) {
+				fprintf(stderr, "cuda_emu: block (%u,%u,%u) appears deadlocked; live fibers:", bx, by, bz);
+				for (int t = 0; t < nthreads; ++t) if (!blk.fibers[t].done) fprintf(stderr, " %d", t);
+				fprintf(stderr, "\n");
+				abort();
+			}
 		}
 	}
 	g_block = saved;

@@ -173,6 +173,22 @@ def test_byte_overflow_falls_back_to_word(engine, ours, checker, capfd):
     assert checker.align(reads[0], ref, mat, 5, 3, 1, 0, 0, 0, 200, score_size=0) is None
 
 
+@pytest.mark.parametrize("flag", [2, 0x0f])
+def test_config5_shape_long_reads(engine, checker, flag, capfd):
+    """Config 5 shape: 10 kbp reads x 100 kbp reference (byte pass overflows -> word), strip-pipelined fill, reverse
+    pass with early termination, banded traceback; every field and every CIGAR word."""
+    ref, reads = C.make_dna_workload(100_000, 12 if C.have_ref() else 2, 10_000, seed_ref=5005, seed_reads=5006,
+                                     decoy_frac=0.0, p_sub=0.05, p_ins=0.02, p_del=0.02)
+    reads.append(reads[0][:3000].copy())                       # ragged batch: a shorter long read
+    reads.append(reads[1][:700].copy())
+    mat = C.dna_matrix(2, 2)
+    engine.set_sequences(reads, [ref])
+    res, pool = engine.align(mat, 5, 3, 1, flag=flag, filters=0, filterd=32767, mask_len=5000, score_size=2)
+    for i, q in enumerate(reads):
+        exp = checker.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, 5000, 2)
+        assert C.diff_results(batch_dict(res, pool, i), exp) == [], (flag, i)
+
+
 def test_edge_cases(ours, checker, capfd):
     """Length-1 sequences, all-N queries, zero score, maskLen < 15, ragged batch."""
     mat = C.dna_matrix(2, 2)
