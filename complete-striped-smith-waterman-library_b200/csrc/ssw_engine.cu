@@ -87,8 +87,7 @@ struct ssw_engine {
 	SswTimer t_total, t_k;
 
 	int upload_refs(int n);
-	int run_fill(const std::vector<SswItem>& items, int inst, int dir, bool write_cm, bool term,
-	             const ssw_batch_params& P, float* ms_acc);
+	int run_fill(const std::vector<SswItem>& items, int inst, int dir, int share, const ssw_batch_params& P, float* ms_acc);
 };
 
 /* ------------------------------------------------------------------------------------------- */
@@ -96,12 +95,12 @@ struct ssw_engine {
 /* ------------------------------------------------------------------------------------------- */
 
 template <int G, int R>
-static int launch_fill(ssw_engine* e, int n_items, int dir, bool write_cm, bool term, const ssw_batch_params& P)
+static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw_batch_params& P)
 {
 	constexpr int GPW = 32 / G;
 	const int per_cta = SSW_FILL_WARPS * GPW;
 	const int grid = (n_items + per_cta - 1) / per_cta;
-	const size_t smem = ssw_fill_smem_bytes<R>(P.n);
+	const size_t smem = ssw_fill_smem_bytes<R>(P.n, share ? 1 : SSW_FILL_WARPS);
 	const SswItem* items = e->d_items.as<SswItem>();
 	const int8_t* q = e->d_q.as<int8_t>();
 	const int8_t* r = e->d_r.as<int8_t>();
@@ -114,9 +113,8 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, bool write_cm, bool 
 		if (smem > 48 * 1024)                                                                                    \
 			SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
 		ssw_launch(kern, dim3(grid), dim3(SSW_FILL_THREADS), smem, e->stream, items, n_items, q, r, mat, (int)P.n, \
-		           (int)P.gap_open, (int)P.gap_extend, cm, bests);                                               \
+		           (int)P.gap_open, (int)P.gap_extend, cm, bests, share);                                        \
 	} while (0)
-	(void)write_cm; (void)term;
 	if (dir > 0) SSW_FILL_GO(1, true, false);          /* forward: column maxima always recorded */
 	else SSW_FILL_GO(-1, false, G == 32);               /* reverse: one alignment per warp, early termination */
 #undef SSW_FILL_GO
@@ -124,8 +122,7 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, bool write_cm, bool 
 	return 0;
 }
 
-int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, bool write_cm, bool term,
-                         const ssw_batch_params& P, float* ms_acc)
+int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, int share, const ssw_batch_params& P, float* ms_acc)
 {
 	const int n_items = (int)items.size();
 	if (n_items == 0) return 0;
@@ -137,17 +134,17 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, b
 	t_k.start(stream);
 	int rc = -1;
 	switch (inst) {
-	case 0: rc = launch_fill<8, 4>(this, n_items, dir, write_cm, term, P); break;
-	case 1: rc = launch_fill<8, 5>(this, n_items, dir, write_cm, term, P); break;
-	case 2: rc = launch_fill<8, 8>(this, n_items, dir, write_cm, term, P); break;
-	case 3: rc = launch_fill<8, 10>(this, n_items, dir, write_cm, term, P); break;
-	case 4: rc = launch_fill<16, 8>(this, n_items, dir, write_cm, term, P); break;
-	case 5: rc = launch_fill<16, 10>(this, n_items, dir, write_cm, term, P); break;
-	case 6: rc = launch_fill<32, 8>(this, n_items, dir, write_cm, term, P); break;
-	case 7: rc = launch_fill<32, 10>(this, n_items, dir, write_cm, term, P); break;
-	case 8: rc = launch_fill<32, 16>(this, n_items, dir, write_cm, term, P); break;
-	case 9: rc = launch_fill<8, 20>(this, n_items, dir, write_cm, term, P); break;
-	case 10: rc = launch_fill<32, 5>(this, n_items, dir, write_cm, term, P); break;
+	case 0: rc = launch_fill<8, 4>(this, n_items, dir, share, P); break;
+	case 1: rc = launch_fill<8, 5>(this, n_items, dir, share, P); break;
+	case 2: rc = launch_fill<8, 8>(this, n_items, dir, share, P); break;
+	case 3: rc = launch_fill<8, 10>(this, n_items, dir, share, P); break;
+	case 4: rc = launch_fill<16, 8>(this, n_items, dir, share, P); break;
+	case 5: rc = launch_fill<16, 10>(this, n_items, dir, share, P); break;
+	case 6: rc = launch_fill<32, 8>(this, n_items, dir, share, P); break;
+	case 7: rc = launch_fill<32, 10>(this, n_items, dir, share, P); break;
+	case 8: rc = launch_fill<32, 16>(this, n_items, dir, share, P); break;
+	case 9: rc = launch_fill<8, 20>(this, n_items, dir, share, P); break;
+	case 10: rc = launch_fill<32, 5>(this, n_items, dir, share, P); break;
 	default: break;
 	}
 	tr.lap("  fill: launch");
@@ -270,10 +267,81 @@ struct Aln {            /* one requested pair while it moves through the phases 
 	int32_t rev_score, rev_pos, rev_row;
 };
 
+/* scoring context of one call */
+struct Sem {
+	int bias, max_mat;
+	int limit_byte;     /* 255 - bias: a byte-semantics score >= this overflows (ssw.c:329) */
+	int limit_word;     /* 16-bit head-room guard */
+	bool has_byte, has_word;
+};
+
 static inline int lp_of(int len, int word) { int g = word ? 8 : 16; return (len + g - 1) / g * g; }
 
-}  // namespace
+/* Does a forward result obtained with semantics `word` have to be replaced by the other semantics?
+ *   byte result that overflowed -> word (ssw.c:883-886)
+ *   word result computed first because an overflow was predicted, but the score fits a byte -> byte */
+static inline bool needs_other(const SswFillResult& r, int word, const Sem& S, bool word_first)
+{
+	if (!word) return r.overflow == 1 && S.has_word;
+	return word_first && S.has_byte && r.overflow == 0 && r.score < S.limit_byte;
+}
 
+/* Launch the resolve kernel over `descs` and fetch the results. */
+static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool second, std::vector<SswFillResult>& res)
+{
+	res.resize(descs.size());
+	if (descs.empty()) return 0;
+	if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
+	if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
+	SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
+	e->t_k.start(e->stream);
+	const int per = SSW_RESOLVE_THREADS / 32;
+	const dim3 grid(((int)descs.size() + per - 1) / per);
+	if (second)
+		ssw_launch(ssw_resolve_kernel<true>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
+		           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)e->d_colmax.as<uint32_t>(), e->d_res.as<SswFillResult>());
+	else
+		ssw_launch(ssw_resolve_kernel<false>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
+		           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)nullptr, e->d_res.as<SswFillResult>());
+	SSW_CUDA_OK(cudaGetLastError());
+	e->timing.resolve_ms += e->t_k.stop(e->stream);
+	e->timing.other_launches += 1;
+	SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
+	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+/*
+ * Forward bookkeeping shared by both fill kernels: resolve `descs` (semantics `word`), then, where the result must
+ * be replaced by the other semantics (needs_other), either re-resolve on the same column maxima -- possible when
+ * both semantics have the same number of pad rows, i.e. the matrices are identical -- or queue the alignment in
+ * `refill` for a fill with the other row count.
+ */
+static int resolve_forward(ssw_engine* e, std::vector<SswAlnDesc>& descs, const std::vector<int64_t>& desc_aln, std::vector<Aln>& alns,
+                           int word, const Sem& S, bool word_first, std::vector<int64_t>* refill)
+{
+	std::vector<SswFillResult> res;
+	if (run_resolve(e, descs, true, res)) return -1;
+	std::vector<SswAlnDesc> alt;
+	std::vector<int64_t> alt_aln;
+	for (size_t i = 0; i < descs.size(); ++i) {
+		Aln& a = alns[desc_aln[i]];
+		a.fwd = res[i]; a.word = word;
+		if (!needs_other(res[i], word, S, word_first)) continue;
+		if (lp_of(a.read_len, 0) == lp_of(a.read_len, 1)) {
+			SswAlnDesc d = descs[i];
+			d.word = !word;
+			d.limit = d.word ? S.limit_word : S.limit_byte;
+			alt.push_back(d);
+			alt_aln.push_back(desc_aln[i]);
+		} else if (refill) refill->push_back(desc_aln[i]);
+	}
+	if (!alt.empty()) {
+		if (run_resolve(e, alt, true, res)) return -1;
+		for (size_t i = 0; i < alt.size(); ++i) { alns[alt_aln[i]].fwd = res[i]; alns[alt_aln[i]].word = alt[i].word; }
+	}
+	return 0;
+}
 
 /* ------------------------------------------------------------------------------------------- */
 /* strip-pipelined fill for queries longer than one strip (ssw_fill_strips_kernel)               */
@@ -285,15 +353,14 @@ struct StripReq {             /* one pair-task (forward) or one alignment (rever
 	int32_t r, cend, p1, term;
 };
 
-/* Launch the strip kernel over `reqs` (all with dir/term alike), resolve, and hand the results back through `sink`. */
+/* Launch the strip kernel over `reqs`; every launch hands its descriptors to `after` (resolve + merge). */
 static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vector<StripReq>& reqs, int dir, bool term,
-                      int word, int limit, const std::vector<Aln>& alns, float* ms_acc,
-                      const std::function<void(int64_t aln, const SswFillResult&)>& sink)
+                      const std::vector<Aln>& alns, float* ms_acc,
+                      const std::function<int(std::vector<SswAlnDesc>&, const std::vector<int64_t>&)>& after)
 {
 	constexpr int R = SSW_STRIP_R;
 	const int rows_per_strip = 32 * R;
 	const size_t warp_smem = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t);
-	size_t k = 0;
 	/* one launch per distinct strip count (it fixes the CTA shape) */
 	std::vector<size_t> order(reqs.size());
 	for (size_t i = 0; i < reqs.size(); ++i) order[i] = i;
@@ -302,6 +369,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		const int sx = strips_of(reqs[x]), sy = strips_of(reqs[y]);
 		return sx != sy ? sx < sy : x < y;
 	});
+	size_t k = 0;
 	while (k < order.size()) {
 		const int n_strips = strips_of(reqs[order[k]]);
 		/* warps per CTA: as many as shared memory allows, preferring a count that divides the strips evenly */
@@ -347,7 +415,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 				d.first_item = n_best; d.n_items = n_strips * T.n_super; d.half = h;
 				d.ref_len = dir > 0 ? T.ref_len : q.p1;
 				d.read_len = h ? q.qb.len : q.qa.len;
-				d.word = word; d.limit = limit; d.mask_len = X.mask_len; d.cm_off = T.cm_off; d.scan_all = 1;
+				d.word = 1; d.limit = 0x7fffffff; d.mask_len = X.mask_len; d.cm_off = T.cm_off; d.scan_all = 1;
 				descs.push_back(d);
 				desc_aln.push_back(h ? q.b : q.a);
 			}
@@ -377,55 +445,42 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		SSW_CUDA_OK(cudaGetLastError());
 		*ms_acc += e->t_k.stop(e->stream);
 		if (dir > 0) e->timing.fill_forward_launches += 1; else e->timing.other_launches += 1;
-
-		if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
-		if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
-		SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
-		e->t_k.start(e->stream);
-		{
-			const int per = SSW_RESOLVE_THREADS / 32;
-			const dim3 grid(((int)descs.size() + per - 1) / per);
-			if (dir > 0)
-				ssw_launch(ssw_resolve_kernel<true>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
-				           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)e->d_colmax.as<uint32_t>(), e->d_res.as<SswFillResult>());
-			else
-				ssw_launch(ssw_resolve_kernel<false>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
-				           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)nullptr, e->d_res.as<SswFillResult>());
-			SSW_CUDA_OK(cudaGetLastError());
-		}
-		e->timing.resolve_ms += e->t_k.stop(e->stream);
-		e->timing.other_launches += 1;
-		std::vector<SswFillResult> res(descs.size());
-		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
-		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
-		for (size_t i = 0; i < descs.size(); ++i) sink(desc_aln[i], res[i]);
+		const int rc = after(descs, desc_aln);
+		if (rc) return rc;
 	}
 	return 0;
 }
 
-/* Plan and run one forward fill + resolve over the alignments `sel` (indices into alns) with the given semantics. */
+/*
+ * One forward fill + bookkeeping over the alignments `sel` with semantics `word` (P1, ssw.c:881-899).
+ * word_first: these alignments were given word semantics on a prediction; results whose score fits a byte are
+ * replaced by byte semantics.  Alignments that need a fill with the other row count are appended to `refill`.
+ */
 static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>& alns, const std::vector<int64_t>& sel,
-                        int word, int bias, int max_mat)
+                        int word, const Sem& S, bool word_first, std::vector<int64_t>* refill)
 {
 	if (sel.empty()) return 0;
 	Trace tr;
-	/* order: kernel instance, reference, then query length so that partners are alike */
-	struct Key { int inst; int32_t r; int32_t lp; int64_t idx; };
-	std::vector<Key> keys;
-	std::vector<Key> long_keys;          /* queries longer than one strip: strip-pipelined kernel */
+	const int limit = word ? S.limit_word : S.limit_byte;
+	struct Key { int inst; int32_t r; int32_t q; int32_t lp; int64_t idx; };
+	std::vector<Key> keys, long_keys;          /* long_keys: queries longer than one strip */
 	for (size_t i = 0; i < sel.size(); ++i) {
 		const Aln& a = alns[sel[i]];
 		const int lp = lp_of(a.read_len, word);
 		const int inst = pick_inst(lp);
-		if (inst < 0) long_keys.push_back(Key{0, a.r, lp, sel[i]});
-		else keys.push_back(Key{inst, a.r, lp, sel[i]});
+		(inst < 0 ? long_keys : keys).push_back(Key{inst < 0 ? 0 : inst, a.r, a.q, lp, sel[i]});
 	}
+	auto by_ref = [](const Key& x, const Key& y) {
+		if (x.inst != y.inst) return x.inst < y.inst;
+		if (x.r != y.r) return x.r < y.r;
+		if (x.lp != y.lp) return x.lp < y.lp;
+		if (x.q != y.q) return x.q < y.q;
+		return x.idx < y.idx;
+	};
+
+	/* ---- long queries: strip-pipelined kernel, one CTA per pair-task ---- */
 	if (!long_keys.empty()) {
-		std::sort(long_keys.begin(), long_keys.end(), [](const Key& x, const Key& y) {
-			if (x.r != y.r) return x.r < y.r;
-			if (x.lp != y.lp) return x.lp < y.lp;
-			return x.idx < y.idx;
-		});
+		std::sort(long_keys.begin(), long_keys.end(), by_ref);
 		std::vector<StripReq> reqs;
 		for (size_t i = 0; i < long_keys.size();) {
 			StripReq q;
@@ -441,24 +496,35 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				++i;
 			}
 			reqs.push_back(q);
-		}
-		const int limit = word ? 32767 - std::max(max_mat, 0) - 256 : 255 - bias;
-		int rc = run_strips(e, P, reqs, +1, false, word, limit, alns, &e->timing.fill_forward_ms,
-		                    [&](int64_t ai, const SswFillResult& r) { alns[ai].fwd = r; alns[ai].word = word; });
-		if (rc) return rc;
-		for (const StripReq& q : reqs) {
 			const int lpmax = std::max(q.qa.lp, q.qb.lp);
 			e->timing.cells_forward += (int64_t)q.p1 * ((lpmax + 32 * SSW_STRIP_R - 1) / (32 * SSW_STRIP_R)) * 32 * SSW_STRIP_R * 2;
 		}
+		const int rc = run_strips(e, P, reqs, +1, false, alns, &e->timing.fill_forward_ms,
+		                          [&](std::vector<SswAlnDesc>& descs, const std::vector<int64_t>& desc_aln) -> int {
+			for (SswAlnDesc& d : descs) { d.word = word; d.limit = limit; }
+			return resolve_forward(e, descs, desc_aln, alns, word, S, word_first, refill);
+		});
+		if (rc) return rc;
 	}
 	if (keys.empty()) return 0;
-	std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
-		if (x.inst != y.inst) return x.inst < y.inst;
-		if (x.r != y.r) return x.r < y.r;
-		if (x.lp != y.lp) return x.lp < y.lp;
-		return x.idx < y.idx;
-	});
 
+	/* ---- queries of one strip: pair-tasks = two alignments on the same reference ---- */
+	std::sort(keys.begin(), keys.end(), by_ref);
+	struct PT { int inst; int64_t a, b; int32_t r, qa, qb; };
+	std::vector<PT> pts;
+	for (size_t i = 0; i < keys.size();) {
+		PT pt; pt.inst = keys[i].inst; pt.a = keys[i].idx; pt.b = -1; pt.r = keys[i].r; pt.qa = keys[i].q; pt.qb = -1;
+		++i;
+		if (i < keys.size() && keys[i].inst == pt.inst && keys[i].r == pt.r) { pt.b = keys[i].idx; pt.qb = keys[i].q; ++i; }
+		pts.push_back(pt);
+	}
+	/* query-pair major order: consecutive items then share their two queries, so a CTA needs one profile */
+	std::sort(pts.begin(), pts.end(), [](const PT& x, const PT& y) {
+		if (x.inst != y.inst) return x.inst < y.inst;
+		if (x.qa != y.qa) return x.qa < y.qa;
+		if (x.qb != y.qb) return x.qb < y.qb;
+		return x.r < y.r;
+	});
 	tr.lap("forward: sort");
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);
@@ -466,61 +532,84 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	tr.lap("forward: memgetinfo");
 
 	size_t k = 0;
-	while (k < keys.size()) {
+	while (k < pts.size()) {
 		/* one launch = one kernel instance, bounded by the column-maximum budget */
-		const int inst = keys[k].inst;
-		std::vector<SswItem> items;
-		std::vector<SswAlnDesc> descs;
-		std::vector<int64_t> desc_aln;
-		size_t cm_words = 0;
-		int64_t cells = 0;
-		/* pass 1: form pair-tasks, decide the chunk length from the amount of work in this launch */
-		struct PT { int64_t a, b; int32_t r; };
-		std::vector<PT> pts;
-		size_t k_end = k;
+		const int inst = pts[k].inst;
+		const int per_cta = SSW_FILL_WARPS * (32 / kInst[inst].G);
+		size_t k_end = k, cm_words = 0;
 		int64_t total_cols = 0;
-		while (k_end < keys.size() && keys[k_end].inst == inst) {
-			const int32_t r = keys[k_end].r;
-			const size_t words = ((size_t)e->r_len[r] + 3) / 4 * 4;
-			if (!pts.empty() && cm_words + words > cm_budget_words) break;
-			PT pt; pt.a = keys[k_end].idx; pt.b = -1; pt.r = r;
-			++k_end;
-			if (k_end < keys.size() && keys[k_end].inst == inst && keys[k_end].r == r) { pt.b = keys[k_end].idx; ++k_end; }
-			pts.push_back(pt);
+		while (k_end < pts.size() && pts[k_end].inst == inst) {
+			const size_t words = ((size_t)e->r_len[pts[k_end].r] + 3) / 4 * 4;
+			if (k_end > k && cm_words + words > cm_budget_words) break;
 			cm_words += words;
-			total_cols += e->r_len[r];
+			total_cols += e->r_len[pts[k_end].r];
+			++k_end;
 		}
 		const int64_t target_items = (int64_t)e->sm_count * 32 * 8;
-		int64_t auto_chunk = (total_cols / target_items + 3) / 4 * 4;
+		const int64_t auto_chunk = (total_cols / target_items + 3) / 4 * 4;
 
-		cm_words = 0;
-		for (const PT& pt : pts) {
+		/* chunk every pair-task; a multi-chunk pair-task gets a multiple of per_cta chunks so that its CTAs are full */
+		struct Plan { int32_t n_chunks, chunk, warm; };
+		std::vector<Plan> plan(k_end - k);
+		int64_t live_items = 0, padded_items = 0, run_items = 0;
+		for (size_t i = k; i < k_end; ++i) {
+			const PT& pt = pts[i];
 			const Aln& A = alns[pt.a];
 			const Aln* B = pt.b >= 0 ? &alns[pt.b] : nullptr;
 			const int32_t ref_len = e->r_len[pt.r];
-			const int lpa = lp_of(A.read_len, word), lpb = B ? lp_of(B->read_len, word) : 0;
-			const int max_lp = std::max(lpa, lpb), max_len = std::max(A.read_len, B ? B->read_len : 0);
+			const int max_lp = std::max(lp_of(A.read_len, word), B ? lp_of(B->read_len, word) : 0);
+			const int max_len = std::max(A.read_len, B ? B->read_len : 0);
 			/* a path with positive score spans at most max_lp diagonal steps plus (total positive score)/gapE gap columns */
 			int64_t warm = 0, chunk = ref_len;
-			if (P.gap_extend > 0 && max_mat > 0) {
-				warm = (int64_t)max_lp + ((int64_t)max_len * max_mat + P.gap_extend - 1) / P.gap_extend + 4;
+			if (P.gap_extend > 0 && S.max_mat > 0) {
+				warm = (int64_t)max_lp + ((int64_t)max_len * S.max_mat + P.gap_extend - 1) / P.gap_extend + 4;
 				warm = (warm + 3) / 4 * 4;
 				chunk = e->opt_chunk > 0 ? e->opt_chunk : std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
 			}
-			if (chunk >= ref_len) chunk = std::max<int32_t>(ref_len, 4);
-			chunk = (chunk + 3) / 4 * 4;
-			const int n_chunks = std::max<int>(1, (int)((ref_len + chunk - 1) / chunk));
+			int64_t n_chunks = chunk >= ref_len ? 1 : (ref_len + chunk - 1) / chunk;
+			if (n_chunks > 1 && e->opt_chunk == 0) {
+				n_chunks = (n_chunks + per_cta - 1) / per_cta * per_cta;
+				chunk = ((ref_len + n_chunks - 1) / n_chunks + 3) / 4 * 4;
+				n_chunks = (ref_len + chunk - 1) / chunk;
+			}
+			if (n_chunks == 1) chunk = std::max<int32_t>((ref_len + 3) / 4 * 4, 4);
+			plan[i - k] = Plan{(int32_t)n_chunks, (int32_t)chunk, (int32_t)warm};
+			live_items += n_chunks;
+			const bool new_run = i == k || pts[i].qa != pts[i - 1].qa || pts[i].qb != pts[i - 1].qb;
+			if (new_run) { padded_items += (run_items + per_cta - 1) / per_cta * per_cta; run_items = 0; }
+			run_items += n_chunks;
+		}
+		padded_items += (run_items + per_cta - 1) / per_cta * per_cta;
+		const int share = padded_items * 100 <= live_items * 112 ? 1 : 0;
+
+		std::vector<SswItem> items;
+		std::vector<SswAlnDesc> descs;
+		std::vector<int64_t> desc_aln;
+		items.reserve((size_t)(share ? padded_items : live_items));
+		int64_t cells = 0;
+		cm_words = 0;
+		for (size_t i = k; i < k_end; ++i) {
+			const PT& pt = pts[i];
+			const Aln& A = alns[pt.a];
+			const Aln* B = pt.b >= 0 ? &alns[pt.b] : nullptr;
+			const int32_t ref_len = e->r_len[pt.r];
+			const Plan& pl = plan[i - k];
+			SswItem it;
+			memset(&it, 0, sizeof(it));
+			it.qa.off = (int32_t)e->q_off[A.q]; it.qa.len = A.read_len; it.qa.lp = lp_of(A.read_len, word); it.qa.rev = 0;
+			if (B) { it.qb.off = (int32_t)e->q_off[B->q]; it.qb.len = B->read_len; it.qb.lp = lp_of(B->read_len, word); it.qb.rev = 0; }
+			it.ref_off = e->r_off[pt.r]; it.ref_len = ref_len; it.term_a = -1;
+			if (share && i > k && (pts[i].qa != pts[i - 1].qa || pts[i].qb != pts[i - 1].qb)) {
+				/* the queries change: fill the current CTA with dead items (empty range) of the previous queries */
+				SswItem dead = items.back();
+				dead.p0 = dead.p1 = 0; dead.warm = 0; dead.cm_off = -1;
+				while (items.size() % (size_t)per_cta) items.push_back(dead);
+			}
 			const int first_item = (int)items.size();
-			for (int c = 0; c < n_chunks; ++c) {
-				SswItem it;
-				memset(&it, 0, sizeof(it));
-				it.qa.off = (int32_t)e->q_off[A.q]; it.qa.len = A.read_len; it.qa.lp = lpa; it.qa.rev = 0;
-				if (B) { it.qb.off = (int32_t)e->q_off[B->q]; it.qb.len = B->read_len; it.qb.lp = lpb; it.qb.rev = 0; }
-				it.ref_off = e->r_off[pt.r]; it.ref_len = ref_len; it.cend = 0;
-				it.p0 = (int32_t)(c * chunk);
-				it.p1 = (int32_t)std::min<int64_t>(ref_len, (c + 1) * chunk);
-				it.warm = (int32_t)std::min<int64_t>(warm, it.p0);
-				it.term_a = -1;
+			for (int c = 0; c < pl.n_chunks; ++c) {
+				it.p0 = (int32_t)((int64_t)c * pl.chunk);
+				it.p1 = (int32_t)std::min<int64_t>(ref_len, (int64_t)(c + 1) * pl.chunk);
+				it.warm = std::min(pl.warm, it.p0);
 				it.cm_off = (int64_t)cm_words;
 				items.push_back(it);
 				cells += (int64_t)(it.p1 - it.p0 + it.warm) * kInst[inst].G * kInst[inst].R * 2;
@@ -529,43 +618,21 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				const Aln& X = h ? *B : A;
 				SswAlnDesc d;
 				memset(&d, 0, sizeof(d));
-				d.first_item = first_item; d.n_items = n_chunks; d.half = h; d.ref_len = ref_len; d.read_len = X.read_len;
-				d.word = word;
-				d.limit = word ? 32767 - std::max(max_mat, 0) - 256 : 255 - bias;   /* 256: head-room for the fill kernel's bias */
-				d.mask_len = X.mask_len; d.cm_off = (int64_t)cm_words;
+				d.first_item = first_item; d.n_items = pl.n_chunks; d.half = h; d.ref_len = ref_len; d.read_len = X.read_len;
+				d.word = word; d.limit = limit; d.mask_len = X.mask_len; d.cm_off = (int64_t)cm_words;
 				descs.push_back(d);
 				desc_aln.push_back(h ? pt.b : pt.a);
 			}
 			cm_words += ((size_t)ref_len + 3) / 4 * 4;
 		}
-
 		tr.lap("forward: plan");
 		if (e->d_colmax.ensure(cm_words * 4 + 64)) return -1;
-		if (e->run_fill(items, inst, +1, true, false, P, &e->timing.fill_forward_ms)) return -1;
+		if (e->run_fill(items, inst, +1, share, P, &e->timing.fill_forward_ms)) return -1;
 		tr.lap("forward: fill (copy+kernel)");
 		e->timing.fill_forward_launches += 1;
 		e->timing.cells_forward += cells;
-
-		/* bookkeeping */
-		if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
-		if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
-		SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
-		e->t_k.start(e->stream);
-		{
-			const int per = SSW_RESOLVE_THREADS / 32;
-			ssw_launch(ssw_resolve_kernel<true>, dim3(((int)descs.size() + per - 1) / per), dim3(SSW_RESOLVE_THREADS), 0, e->stream,
-			           (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(), (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(),
-			           (const uint32_t*)e->d_colmax.as<uint32_t>(), e->d_res.as<SswFillResult>());
-			SSW_CUDA_OK(cudaGetLastError());
-		}
-		e->timing.resolve_ms += e->t_k.stop(e->stream);
-		tr.lap("forward: resolve kernel");
-		e->timing.other_launches += 1;
-		std::vector<SswFillResult> res(descs.size());
-		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
-		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
-		for (size_t i = 0; i < descs.size(); ++i) { alns[desc_aln[i]].fwd = res[i]; alns[desc_aln[i]].word = word; }
-		tr.lap("forward: resolve + d2h");
+		if (resolve_forward(e, descs, desc_aln, alns, word, S, word_first, refill)) return -1;
+		tr.lap("forward: resolve");
 		k = k_end;
 	}
 	return 0;
@@ -588,9 +655,18 @@ static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 		q.qa.off = (int32_t)e->q_off[a.q]; q.qa.len = a.fwd.read + 1; q.qa.lp = lp_of(q.qa.len, a.word); q.qa.rev = 1;
 		long_reqs.push_back(q);
 	}
+	auto merge = [&](const std::vector<SswAlnDesc>& descs, const std::vector<int64_t>& desc_aln) -> int {
+		std::vector<SswFillResult> res;
+		if (run_resolve(e, descs, false, res)) return -1;
+		for (size_t i = 0; i < descs.size(); ++i) {
+			Aln& a = alns[desc_aln[i]];
+			a.rev_score = res[i].score; a.rev_pos = res[i].ref; a.rev_row = res[i].read;
+		}
+		return 0;
+	};
 	if (!long_reqs.empty()) {
-		int rc = run_strips(e, P, long_reqs, -1, true, 1, 0x7fffffff, alns, &e->timing.fill_reverse_ms,
-		                    [&](int64_t ai, const SswFillResult& r) { alns[ai].rev_score = r.score; alns[ai].rev_pos = r.ref; alns[ai].rev_row = r.read; });
+		const int rc = run_strips(e, P, long_reqs, -1, true, alns, &e->timing.fill_reverse_ms,
+		                          [&](std::vector<SswAlnDesc>& descs, const std::vector<int64_t>& desc_aln) -> int { return merge(descs, desc_aln); });
 		if (rc) return rc;
 	}
 	std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.inst != y.inst ? x.inst < y.inst : x.idx < y.idx; });
@@ -615,31 +691,14 @@ static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			descs.push_back(d);
 			desc_aln.push_back(keys[k].idx);
 		}
-		if (e->run_fill(items, inst, -1, false, true, P, &e->timing.fill_reverse_ms)) return -1;
+		if (e->run_fill(items, inst, -1, 0, P, &e->timing.fill_reverse_ms)) return -1;
 		e->timing.other_launches += 1;
-		if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
-		if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
-		SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
-		e->t_k.start(e->stream);
-		{
-			const int per = SSW_RESOLVE_THREADS / 32;
-			ssw_launch(ssw_resolve_kernel<false>, dim3(((int)descs.size() + per - 1) / per), dim3(SSW_RESOLVE_THREADS), 0, e->stream,
-			           (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(), (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(),
-			           (const uint32_t*)nullptr, e->d_res.as<SswFillResult>());
-			SSW_CUDA_OK(cudaGetLastError());
-		}
-		e->timing.resolve_ms += e->t_k.stop(e->stream);
-		e->timing.other_launches += 1;
-		std::vector<SswFillResult> res(descs.size());
-		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
-		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
-		for (size_t i = 0; i < descs.size(); ++i) {
-			Aln& a = alns[desc_aln[i]];
-			a.rev_score = res[i].score; a.rev_pos = res[i].ref; a.rev_row = res[i].read;
-		}
+		if (merge(descs, desc_aln)) return -1;
 	}
 	return 0;
 }
+
+}  // namespace
 
 extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
                                 int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
@@ -663,16 +722,19 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 	e->t_total.start(e->stream);
 
 	/* scoring matrix: bias = |min(mat)| for byte semantics (ssw.c:834-838) */
-	int bias = 0, max_mat = -128;
-	for (int i = 0; i < P.n * P.n; ++i) { if (P.mat[i] < bias) bias = P.mat[i]; if (P.mat[i] > max_mat) max_mat = P.mat[i]; }
-	bias = bias < 0 ? -bias : bias;
+	Sem S;
+	S.bias = 0; S.max_mat = -128;
+	for (int i = 0; i < P.n * P.n; ++i) { if (P.mat[i] < S.bias) S.bias = P.mat[i]; if (P.mat[i] > S.max_mat) S.max_mat = P.mat[i]; }
+	S.bias = S.bias < 0 ? -S.bias : S.bias;
+	S.limit_byte = 255 - S.bias;
+	S.limit_word = 32767 - std::max(S.max_mat, 0) - 256;
+	S.has_byte = P.score_size == 0 || P.score_size == 2;
+	S.has_word = P.score_size == 1 || P.score_size == 2;
 	if (e->d_mat.ensure((size_t)P.n * P.n + 16)) return -1;
 	SSW_CUDA_OK(cudaMemcpyAsync(e->d_mat.p, P.mat, (size_t)P.n * P.n, cudaMemcpyHostToDevice, e->stream));
 	if (e->upload_refs(P.n)) return -1;
 
-	const bool has_byte = P.score_size == 0 || P.score_size == 2, has_word = P.score_size == 1 || P.score_size == 2;
 	std::vector<Aln> alns((size_t)n_pairs);
-	std::vector<int64_t> all((size_t)n_pairs);
 	for (int64_t p = 0; p < n_pairs; ++p) {
 		Aln& a = alns[p];
 		a.q = pair_query ? pair_query[p] : (int32_t)(p / e->n_r);
@@ -683,32 +745,41 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 		a.mask_len = P.mask_len < 0 ? a.read_len / 2 : P.mask_len;
 		a.word = 0; a.rev_score = 0; a.rev_pos = 0; a.rev_row = 0;
 		memset(&a.fwd, 0, sizeof(a.fwd));
-		all[p] = p;
 		if (a.read_len < 1) { fprintf(stderr, "[libssw-b200] pair %lld: empty query\n", (long long)p); return -1; }
 	}
-	if (!has_byte && !has_word) {
+	if (!S.has_byte && !S.has_word) {
 		fprintf(stderr, "Please call the function ssw_init before ssw_align.\n");
 		for (int64_t p = 0; p < n_pairs; ++p) { memset(&results[p], 0, sizeof(results[p])); results[p].status = 1; results[p].cigar_off = -1; }
 		return 0;
 	}
 
-	/* ---- P1 ---- */
-	int rc = forward_pass(e, P, alns, all, has_byte ? 0 : 1, bias, max_mat);
-	if (rc) return rc;
-	std::vector<int64_t> redo;
-	std::vector<uint8_t> null_result((size_t)n_pairs, 0);
-	if (has_byte) {
-		for (int64_t p = 0; p < n_pairs; ++p)
-			if (alns[p].fwd.overflow == 1) { if (has_word) redo.push_back(p); else null_result[p] = 1; }
-		e->timing.byte_overflows = (int64_t)redo.size();
-		rc = forward_pass(e, P, alns, redo, 1, bias, max_mat);
-		if (rc) return rc;
+	/* ---- P1 (ssw.c:881-899).  The reference tries byte semantics first and re-runs with word semantics on
+	 * overflow.  The outcome only depends on the final score, so where a byte overflow is certain to be likely
+	 * (the query could score twice the byte limit) word semantics are tried first; either way a result that the
+	 * other semantics must replace is re-resolved on the same matrix or, if the pad rows differ, re-filled. ---- */
+	std::vector<int64_t> byte_first, word_first, refill_word, refill_byte;
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		const bool predict = S.has_byte && S.has_word && (int64_t)alns[p].read_len * std::max(S.max_mat, 0) >= 2 * (int64_t)S.limit_byte;
+		if (!S.has_byte || predict) word_first.push_back(p); else byte_first.push_back(p);
 	}
-	for (int64_t p = 0; p < n_pairs; ++p)
-		if (!null_result[p] && alns[p].fwd.overflow == 2) {
+	int rc = forward_pass(e, P, alns, byte_first, 0, S, false, &refill_word);
+	if (rc) return rc;
+	rc = forward_pass(e, P, alns, word_first, 1, S, S.has_byte, &refill_byte);
+	if (rc) return rc;
+	rc = forward_pass(e, P, alns, refill_word, 1, S, false, nullptr);
+	if (rc) return rc;
+	rc = forward_pass(e, P, alns, refill_byte, 0, S, false, nullptr);
+	if (rc) return rc;
+	std::vector<uint8_t> null_result((size_t)n_pairs, 0);
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		const Aln& a = alns[p];
+		if (a.word == 0 && a.fwd.overflow == 1) { null_result[p] = 1; continue; }    /* byte overflow without a word profile (ssw.c:887-890) */
+		if (a.word == 1 && S.has_byte && a.fwd.score >= S.limit_byte) e->timing.byte_overflows += 1;
+		if (a.fwd.overflow == 2) {
 			fprintf(stderr, "[libssw-b200] pair %lld: score reaches the 16-bit limit; not supported\n", (long long)p);
 			return -4;
 		}
+	}
 
 	/* ---- gating (ssw.c:900-916) and P2 ---- */
 	std::vector<int64_t> need_begin;

@@ -102,7 +102,8 @@ static inline size_t ssw_fill_smem_bytes(int n, int warps = SSW_FILL_WARPS) { re
  * rows beyond the query's padded length and the null letter n score -32768 (dead: H stays 0). */
 template <int R>
 __device__ static __forceinline__ void ssw_build_profile(uint32_t* prof, int lane, int row0, const SswQuery& qa, const SswQuery& qb,
-                                                        const int8_t* __restrict__ qcodes, const int8_t* __restrict__ mat, int n)
+                                                        const int8_t* __restrict__ qcodes, const int8_t* __restrict__ mat, int n,
+                                                        int letter0 = 0, int letter_step = 1)
 {
 	int ca[R], cb[R];
 #pragma unroll
@@ -111,7 +112,7 @@ __device__ static __forceinline__ void ssw_build_profile(uint32_t* prof, int lan
 		ca[k] = row < qa.len ? (int)qcodes[qa.off + (qa.rev ? qa.len - 1 - row : row)] : (row < qa.lp ? -1 : -2);
 		cb[k] = row < qb.len ? (int)qcodes[qb.off + (qb.rev ? qb.len - 1 - row : row)] : (row < qb.lp ? -1 : -2);
 	}
-	for (int letter = 0; letter <= n; ++letter) {
+	for (int letter = letter0; letter <= n; letter += letter_step) {
 		uint32_t* pl = prof + letter * (32 * R);
 #pragma unroll
 		for (int k = 0; k < R; ++k) {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(SSW_FILL_THREADS)
 ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
                 const int8_t* __restrict__ mat, int n, int gapO, int gapE,
-                uint32_t* __restrict__ colmax, SswItemBest* __restrict__ bests)
+                uint32_t* __restrict__ colmax, SswItemBest* __restrict__ bests, int share)
 {
 	static_assert(G == 8 || G == 16 || G == 32, "group width");
 	static_assert(R % 4 != 3 && R >= 1 && R <= 20, "rows per lane");
@@ -235,7 +236,9 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	SSW_DYN_SMEM(uint32_t, smem);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int g = lane / G, t = lane % G;
-	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
+	/* share != 0: the host guarantees that all items of this CTA have the same two queries, so one profile serves
+	 * every warp (built cooperatively); otherwise each warp keeps the profile(s) of its own groups */
+	uint32_t* prof = share ? smem : smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
 
 	const int item_idx = ((int)blockIdx.x * SSW_FILL_WARPS + warp) * GPW + g;
 	const bool live = item_idx < n_items;
@@ -246,8 +249,14 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		it.ref_off = SSW_REF_PAD; it.ref_len = 0; it.cend = 0; it.p0 = it.p1 = 0; it.warm = 0; it.term_a = -1; it.cm_off = -1;
 	}
 
-	ssw_build_profile<R>(prof, lane, t * R, it.qa, it.qb, qcodes, mat, n);
-	__syncwarp();
+	if (share) {
+		const SswItem& first = items[(int)blockIdx.x * SSW_FILL_WARPS * GPW];     /* always a live item */
+		ssw_build_profile<R>(prof, lane, t * R, first.qa, first.qb, qcodes, mat, n, warp, SSW_FILL_WARPS);
+		__syncthreads();
+	} else {
+		ssw_build_profile<R>(prof, lane, t * R, it.qa, it.qb, qcodes, mat, n);
+		__syncwarp();
+	}
 
 	/* ---- sweep ---- */
 	const uint8_t* rp = reinterpret_cast<const uint8_t*>(refs) + it.ref_off;   /* reference column 0 */

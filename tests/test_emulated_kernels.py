@@ -105,3 +105,39 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
             assert C.diff_results(got, exp) == [], (flag, i)
     eng.set_option("super", 0)
     eng.close()
+
+
+def test_emulated_batch_grid_mixed_lengths(oracle, capfd):
+    """The batch ABI on a queries x references grid with ragged lengths: pair-task formation, CTA-shared profiles,
+    word-first prediction (long queries) with fall-back to byte semantics, byte->word re-resolve and re-fill."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    rng = np.random.default_rng(2024)
+    mat = C.dna_matrix(2, 2)
+    refs = [rng.integers(0, 4, size=n).astype(np.int8) for n in (300, 517, 90)]
+    qlens = (16, 40, 40, 150, 152, 260, 272, 300, 33, 7)
+    queries = []
+    for i, n in enumerate(qlens):
+        r = refs[i % len(refs)]
+        if len(r) > n + 20 and i % 3 != 2:
+            queries.append(C.mutate_read(rng, r, int(rng.integers(0, len(r) - n - 10)), n, 0.04 if n > 200 else 0.12, 0.01, 0.01))
+        else:
+            queries.append(rng.integers(0, 4, size=n).astype(np.int8))
+    eng.set_sequences(queries, refs)
+    for score_size in (2, 1, 0):
+        for flag in (0, 9):
+            res, pool = eng.align(mat, 5, 3, 1, flag=flag, filterd=32767, mask_len=-1, score_size=score_size)
+            k = 0
+            for q in queries:
+                for r in refs:
+                    exp = oracle.align(q, r, mat, 5, 3, 1, flag, 0, 32767, len(q) // 2, score_size)
+                    rr = res[k]
+                    if exp is None:
+                        assert int(rr["status"]) == 1, (score_size, flag, k)
+                    else:
+                        got = {f: int(rr[f]) for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
+                        got["cigar"] = [int(x) for x in pool[rr["cigar_off"]: rr["cigar_off"] + rr["cigar_len"]]] if rr["cigar_off"] >= 0 else []
+                        assert int(rr["status"]) == 0 and C.diff_results(got, exp) == [], (score_size, flag, k)
+                    k += 1
+    eng.close()
