@@ -23,6 +23,7 @@
 #include "ssw_fill.cuh"
 #include "ssw_resolve.cuh"
 #include "ssw_traceback.cuh"
+#include "ssw_emul.cuh"
 #include "../../include/ssw_batch.h"
 
 #include <chrono>
@@ -81,7 +82,7 @@ struct ssw_engine {
 	SswDevBuf d_q, d_r, d_mat;
 
 	/* scratch */
-	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park;
+	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul;
 	int64_t opt_chunk = 0;
 	ssw_engine_timing timing;
 	SswTimer t_total, t_k;
@@ -184,7 +185,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 {
 	if (!e) return;
 	cudaSetDevice(e->device);
-	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park};
+	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul};
 	for (SswDevBuf* b : bufs) b->release();
 	if (e->stream) cudaStreamDestroy(e->stream);
 	delete e;
@@ -698,6 +699,75 @@ static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	return 0;
 }
 
+
+/* ------------------------------------------------------------------------------------------- */
+/* layout-literal slow path (ssw_emul_kernel): gapO <= gapE, and word scores near saturation     */
+/* ------------------------------------------------------------------------------------------- */
+
+/* dir 0: forward fill of alns[sel] with semantics `word`; dir 1: begin search (reverse) of alns[sel]. */
+static int emul_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>& alns, const std::vector<int64_t>& sel,
+                     int word, int dir, const Sem& S)
+{
+	if (sel.empty()) return 0;
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + e->d_emul.cap) / 2);
+	size_t k = 0;
+	while (k < sel.size()) {
+		std::vector<SswEmulTask> tasks;
+		std::vector<int64_t> task_aln;
+		size_t state_words = 0, cm_elems = 0;
+		for (; k < sel.size(); ++k) {
+			const Aln& a = alns[sel[k]];
+			const int w = dir ? a.word : word;
+			const int L = w ? 8 : 16;
+			SswEmulTask T;
+			memset(&T, 0, sizeof(T));
+			T.q_off = (int32_t)e->q_off[a.q];
+			T.q_len = dir ? a.fwd.read + 1 : a.read_len;
+			T.q_rev = dir;
+			T.ref_len = dir ? a.fwd.ref + 1 : a.ref_len;
+			T.ref_off = e->r_off[a.r];
+			T.dir = dir; T.word = w;
+			T.terminate = dir ? a.fwd.score : (w ? 65535 : 255);
+			T.bias = S.bias; T.mask_len = a.mask_len;
+			const size_t st = 4 * (size_t)((T.q_len + L - 1) / L) * L;
+			const size_t cm = ((size_t)T.ref_len + 7) / 8 * 8;
+			if (!tasks.empty() && 4 * (state_words + st) + 2 * (cm_elems + cm) > budget) break;
+			T.state_off = (int64_t)state_words; T.cm_off = (int64_t)cm_elems;
+			state_words += st; cm_elems += cm;
+			tasks.push_back(T);
+			task_aln.push_back(sel[k]);
+		}
+		const size_t off_cm = (state_words * 4 + 255) / 256 * 256;
+		const size_t off_tasks = off_cm + (cm_elems * 2 + 255) / 256 * 256;
+		const size_t off_res = off_tasks + (sizeof(SswEmulTask) * tasks.size() + 255) / 256 * 256;
+		if (e->d_emul.ensure(off_res + sizeof(SswFillResult) * tasks.size())) return -1;
+		uint8_t* base = e->d_emul.as<uint8_t>();
+		SSW_CUDA_OK(cudaMemsetAsync(base + off_cm, 0, cm_elems * 2, e->stream));
+		SSW_CUDA_OK(cudaMemcpyAsync(base + off_tasks, tasks.data(), sizeof(SswEmulTask) * tasks.size(), cudaMemcpyHostToDevice, e->stream));
+		e->t_k.start(e->stream);
+		ssw_launch(ssw_emul_kernel, dim3(((int)tasks.size() + SSW_EMUL_WARPS - 1) / SSW_EMUL_WARPS), dim3(SSW_EMUL_THREADS), 0, e->stream,
+		           (const SswEmulTask*)reinterpret_cast<SswEmulTask*>(base + off_tasks), (int)tasks.size(),
+		           (const int8_t*)e->d_q.as<int8_t>(), (const int8_t*)e->d_r.as<int8_t>(), (const int8_t*)e->d_mat.as<int8_t>(), (int)P.n,
+		           (int)P.gap_open, (int)P.gap_extend, reinterpret_cast<int32_t*>(base), reinterpret_cast<uint16_t*>(base + off_cm),
+		           reinterpret_cast<SswFillResult*>(base + off_res));
+		SSW_CUDA_OK(cudaGetLastError());
+		const float ms = e->t_k.stop(e->stream);
+		if (dir) { e->timing.fill_reverse_ms += ms; e->timing.other_launches += 1; }
+		else { e->timing.fill_forward_ms += ms; e->timing.fill_forward_launches += 1; }
+		std::vector<SswFillResult> res(tasks.size());
+		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), base + off_res, sizeof(SswFillResult) * tasks.size(), cudaMemcpyDeviceToHost, e->stream));
+		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+		for (size_t i = 0; i < tasks.size(); ++i) {
+			Aln& a = alns[task_aln[i]];
+			if (dir) { a.rev_score = res[i].score; a.rev_pos = a.fwd.ref - res[i].ref; a.rev_row = res[i].read; }
+			else { a.fwd = res[i]; a.word = word; }
+		}
+	}
+	return 0;
+}
+
 }  // namespace
 
 extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
@@ -715,10 +785,8 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 	SSW_CUDA_OK(cudaSetDevice(e->device));
 	memset(&e->timing, 0, sizeof(e->timing));
 	if (n_pairs == 0) return 0;
-	if (P.gap_open <= P.gap_extend) {
-		fprintf(stderr, "[libssw-b200] gap_open <= gap_extend (%d <= %d): this parameter regime is not implemented yet\n", P.gap_open, P.gap_extend);
-		return -3;
-	}
+	/* gapO <= gapE: the reference's result depends on its SIMD layout (lazy-F exit); use the lane-literal kernel */
+	const bool literal = P.gap_open <= P.gap_extend;
 	e->t_total.start(e->stream);
 
 	/* scoring matrix: bias = |min(mat)| for byte semantics (ssw.c:834-838) */
@@ -762,23 +830,38 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 		const bool predict = S.has_byte && S.has_word && (int64_t)alns[p].read_len * std::max(S.max_mat, 0) >= 2 * (int64_t)S.limit_byte;
 		if (!S.has_byte || predict) word_first.push_back(p); else byte_first.push_back(p);
 	}
-	int rc = forward_pass(e, P, alns, byte_first, 0, S, false, &refill_word);
-	if (rc) return rc;
-	rc = forward_pass(e, P, alns, word_first, 1, S, S.has_byte, &refill_byte);
-	if (rc) return rc;
-	rc = forward_pass(e, P, alns, refill_word, 1, S, false, nullptr);
-	if (rc) return rc;
-	rc = forward_pass(e, P, alns, refill_byte, 0, S, false, nullptr);
-	if (rc) return rc;
+	int rc = 0;
+	if (literal) {
+		std::vector<int64_t> all((size_t)n_pairs), redo;
+		for (int64_t p = 0; p < n_pairs; ++p) all[p] = p;
+		rc = emul_pass(e, P, alns, all, S.has_byte ? 0 : 1, 0, S);
+		if (rc) return rc;
+		if (S.has_byte && S.has_word) {
+			for (int64_t p = 0; p < n_pairs; ++p) if (alns[p].fwd.overflow == 1) redo.push_back(p);
+			rc = emul_pass(e, P, alns, redo, 1, 0, S);
+			if (rc) return rc;
+			e->timing.byte_overflows = (int64_t)redo.size();
+		}
+	} else {
+		rc = forward_pass(e, P, alns, byte_first, 0, S, false, &refill_word);
+		if (rc) return rc;
+		rc = forward_pass(e, P, alns, word_first, 1, S, S.has_byte, &refill_byte);
+		if (rc) return rc;
+		rc = forward_pass(e, P, alns, refill_word, 1, S, false, nullptr);
+		if (rc) return rc;
+		rc = forward_pass(e, P, alns, refill_byte, 0, S, false, nullptr);
+		if (rc) return rc;
+		/* word scores within reach of the 16-bit saturation of the reference (ssw.c:483): literal kernel */
+		std::vector<int64_t> sat;
+		for (int64_t p = 0; p < n_pairs; ++p) if (alns[p].fwd.overflow == 2) sat.push_back(p);
+		rc = emul_pass(e, P, alns, sat, 1, 0, S);
+		if (rc) return rc;
+	}
 	std::vector<uint8_t> null_result((size_t)n_pairs, 0);
 	for (int64_t p = 0; p < n_pairs; ++p) {
 		const Aln& a = alns[p];
 		if (a.word == 0 && a.fwd.overflow == 1) { null_result[p] = 1; continue; }    /* byte overflow without a word profile (ssw.c:887-890) */
-		if (a.word == 1 && S.has_byte && a.fwd.score >= S.limit_byte) e->timing.byte_overflows += 1;
-		if (a.fwd.overflow == 2) {
-			fprintf(stderr, "[libssw-b200] pair %lld: score reaches the 16-bit limit; not supported\n", (long long)p);
-			return -4;
-		}
+		if (!literal && a.word == 1 && S.has_byte && a.fwd.score >= S.limit_byte) e->timing.byte_overflows += 1;
 	}
 
 	/* ---- gating (ssw.c:900-916) and P2 ---- */
@@ -789,8 +872,15 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 		if (P.flag == 0 || (P.flag == 2 && a.fwd.score < P.filters)) continue;
 		need_begin.push_back(p);
 	}
-	rc = reverse_pass(e, P, alns, need_begin);
-	if (rc) return rc;
+	{
+		/* begin search: literal kernel where the forward result came from it (saturating scores) or the regime demands it */
+		std::vector<int64_t> rev_fast, rev_lit;
+		for (int64_t p : need_begin) (literal || alns[p].fwd.score >= S.limit_word ? rev_lit : rev_fast).push_back(p);
+		rc = reverse_pass(e, P, alns, rev_fast);
+		if (rc) return rc;
+		rc = emul_pass(e, P, alns, rev_lit, 1, 1, S);
+		if (rc) return rc;
+	}
 
 	/* ---- assemble the fixed-size records ---- */
 	std::vector<uint8_t> has_begin((size_t)n_pairs, 0);

@@ -49,10 +49,8 @@ def test_emulated_random_vs_oracle(emu, oracle, capfd):
     rng = np.random.default_rng(424242)
     bad = []
     n = 0
-    while n < 120:
-        c = random_case(rng)
-        if c["gapO"] <= c["gapE"]:
-            continue
+    while n < 150:
+        c = random_case(rng)           # every gap regime, incl. gapO <= gapE (lane-literal kernel)
         n += 1
         d = C.diff_results(emu.align(**c), oracle.align(**c))
         if d:
@@ -141,3 +139,16 @@ def test_emulated_batch_grid_mixed_lengths(oracle, capfd):
                         assert int(rr["status"]) == 0 and C.diff_results(got, exp) == [], (score_size, flag, k)
                     k += 1
     eng.close()
+
+
+def test_emulated_word_saturation(emu, oracle, capfd):
+    """Scores that reach the reference's signed 16-bit saturation (ssw.c:483) go through the lane-literal kernel."""
+    rng = np.random.default_rng(1)
+    mat = C.dna_matrix(127, 100)
+    r = rng.integers(0, 4, size=500).astype(np.int8)
+    for qlen, flag, ss in ((300, 0, 1), (290, 15, 2), (256, 1, 2)):
+        q = r[60:60 + qlen].copy()
+        q[qlen // 2] = (q[qlen // 2] + 1) % 4
+        a = emu.align(q, r, mat, 5, 40, 3, flag, 0, 32767, 50, ss)
+        b = oracle.align(q, r, mat, 5, 40, 3, flag, 0, 32767, 50, ss)
+        assert b["score1"] >= 32000 and C.diff_results(a, b) == [], (qlen, flag, ss)

@@ -82,9 +82,7 @@ def test_random_pairs_vs_checker(ours, checker, capfd):
     bad = []
     n = 0
     while n < 1500:
-        c = random_case(rng)
-        if c["gapO"] <= c["gapE"]:
-            continue
+        c = random_case(rng)           # every gap regime, incl. gapO <= gapE (lane-literal kernel)
         n += 1
         a = ours.align(mark=True, **c)
         b = checker.align(mark=True, **c)
@@ -187,6 +185,28 @@ def test_config5_shape_long_reads(engine, checker, flag, capfd):
     for i, q in enumerate(reads):
         exp = checker.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, 5000, 2)
         assert C.diff_results(batch_dict(res, pool, i), exp) == [], (flag, i)
+
+
+def test_word_saturation_and_linear_gaps(ours, engine, checker, capfd):
+    """(i) scores at the reference's signed 16-bit saturation (ssw.c:483); (ii) gapO == gapE on the config-2 shape:
+    both are served by the lane-literal kernel and must match the reference exactly."""
+    rng = np.random.default_rng(1)
+    mat = C.dna_matrix(127, 100)
+    r = rng.integers(0, 4, size=700).astype(np.int8)
+    for qlen, flag, ss in ((300, 0, 1), (300, 15, 2), (280, 8, 1), (256, 1, 2), (330, 0, 2)):
+        q = r[100:100 + qlen].copy()
+        q[qlen // 2] = (q[qlen // 2] + 1) % 4
+        a = ours.align(q, r, mat, 5, 40, 3, flag, 0, 32767, 50, ss)
+        b = checker.align(q, r, mat, 5, 40, 3, flag, 0, 32767, 50, ss)
+        assert C.diff_results(a, b) == [], (qlen, flag, ss)
+    ref, reads = C.make_dna_workload(60_000, 24, 150, seed_ref=77, seed_reads=78)
+    m2 = C.dna_matrix(2, 2)
+    engine.set_sequences(reads, [ref])
+    for gapO, gapE in ((2, 2), (1, 3)):
+        res, pool = engine.align(m2, 5, gapO, gapE, flag=0x0f, filterd=32767, mask_len=75, score_size=2)
+        for i, q in enumerate(reads):
+            exp = checker.align(q, ref, m2, 5, gapO, gapE, 0x0f, 0, 32767, 75, 2)
+            assert C.diff_results(batch_dict(res, pool, i), exp) == [], (gapO, gapE, i)
 
 
 def test_edge_cases(ours, checker, capfd):
