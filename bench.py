@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--inst", type=int, default=-1, help="experiment: force a fill-kernel instance")
     ap.add_argument("--chunk", type=int, default=0, help="experiment: reference chunk length")
     ap.add_argument("--mode", type=int, default=-1, help="experiment: fill arithmetic (0 all-DPX, 1 biased + IMAD)")
+    ap.add_argument("--lib", default="libssw.so", help="experiment: alternative build of the library")
     return ap.parse_args()
 
 
@@ -183,7 +184,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ref, reads, mat = workload(args, rank)
     cells_rank = float(sum(len(q) for q in reads)) * len(ref)
-    eng = L.BatchAligner(device=local)
+    eng = L.BatchAligner(device=local, lib_name=args.lib)
     if args.inst >= 0:
         eng.set_option("inst", args.inst)
     if args.chunk:

@@ -40,26 +40,30 @@ struct Trace {
 	}
 };
 
-/* kernel instance = (lanes per group, rows per lane); rows covered = G*R */
+/* kernel instance = (lanes per group, rows per lane); rows covered = G*R.  Forward instances favour many rows per
+ * lane (fewer shuffles and profile loads per cell; measured on config 2: (8,20) 134 ms, (16,10) 139 ms, (32,5) 178 ms). */
 struct Inst { int G, R; };
 static const Inst kInst[] = {
-	{8, 4}, {8, 5}, {8, 8}, {8, 10}, {16, 8}, {16, 10}, {32, 8}, {32, 10}, {32, 16}, {8, 20}, {32, 5},
+	{8, 4}, {8, 5}, {8, 8}, {8, 10}, {8, 16}, {8, 20}, {16, 16}, {16, 20}, {32, 16}, {32, 20},      /* 0..9: forward, by rows */
+	{32, 4}, {32, 5}, {32, 8}, {32, 10},                                                            /* 10..13: reverse only (one alignment per warp) */
+	{16, 10}, {32, 10},                                                                             /* 14, 15: experiment instances ("inst" option) */
 };
+static const int kNumFwd = 10;
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
-static const int kMaxRows = 512;
 
 static int g_strip_super = SSW_STRIP_SUPER;   /* columns per super-block of the strip kernel ("super" option, tests) */
 static int g_force_inst = -1;      /* experiment knob ("inst" option): use this instance whenever it covers the query */
 static int pick_inst(int lp)
 {
 	if (g_force_inst >= 0 && g_force_inst < kNumInst && kInst[g_force_inst].G * kInst[g_force_inst].R >= lp) return g_force_inst;
-	for (int i = 0; i < 9; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
+	for (int i = 0; i < kNumFwd; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
 	return -1;
 }
 /* reverse pass: one alignment per warp */
 static int pick_inst_g32(int lp)
 {
-	for (int i = 0; i < 9; ++i) if (kInst[i].G == 32 && kInst[i].G * kInst[i].R >= lp) return i;
+	static const int order[] = {10, 11, 12, 13, 8, 9};
+	for (int i : order) if (kInst[i].G * kInst[i].R >= lp) return i;
 	return -1;
 }
 
@@ -99,9 +103,14 @@ template <int G, int R>
 static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw_batch_params& P)
 {
 	constexpr int GPW = 32 / G;
-	const int per_cta = SSW_FILL_WARPS * GPW;
+	/* per-warp profiles (share == 0) can be large for big alphabets: use fewer warps per CTA then */
+	const size_t warp_smem = ssw_fill_smem_bytes<R>(P.n, 1);
+	int warps = SSW_FILL_WARPS;
+	if (!share) while (warps > 1 && warp_smem * warps > 200 * 1024) --warps;
+	const int per_cta = warps * GPW;
 	const int grid = (n_items + per_cta - 1) / per_cta;
-	const size_t smem = ssw_fill_smem_bytes<R>(P.n, share ? 1 : SSW_FILL_WARPS);
+	const size_t smem = share ? warp_smem : warp_smem * warps;
+	if (smem > 220 * 1024) { fprintf(stderr, "[libssw-b200] alphabet of %d letters is too large for this query length\n", P.n); return -2; }
 	const SswItem* items = e->d_items.as<SswItem>();
 	const int8_t* q = e->d_q.as<int8_t>();
 	const int8_t* r = e->d_r.as<int8_t>();
@@ -113,11 +122,14 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw
 		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM>;                                                        \
 		if (smem > 48 * 1024)                                                                                    \
 			SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-		ssw_launch(kern, dim3(grid), dim3(SSW_FILL_THREADS), smem, e->stream, items, n_items, q, r, mat, (int)P.n, \
+		ssw_launch(kern, dim3(grid), dim3(warps * 32), smem, e->stream, items, n_items, q, r, mat, (int)P.n,     \
 		           (int)P.gap_open, (int)P.gap_extend, cm, bests, share);                                        \
 	} while (0)
-	if (dir > 0) SSW_FILL_GO(1, true, false);          /* forward: column maxima always recorded */
-	else SSW_FILL_GO(-1, false, G == 32);               /* reverse: one alignment per warp, early termination */
+	if (dir > 0) SSW_FILL_GO(1, true, false);           /* forward: column maxima always recorded */
+	else {
+		if constexpr (G == 32) SSW_FILL_GO(-1, false, true);   /* reverse: one alignment per warp, early termination */
+		else return -2;
+	}
 #undef SSW_FILL_GO
 	SSW_CUDA_OK(cudaGetLastError());
 	return 0;
@@ -139,13 +151,18 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, i
 	case 1: rc = launch_fill<8, 5>(this, n_items, dir, share, P); break;
 	case 2: rc = launch_fill<8, 8>(this, n_items, dir, share, P); break;
 	case 3: rc = launch_fill<8, 10>(this, n_items, dir, share, P); break;
-	case 4: rc = launch_fill<16, 8>(this, n_items, dir, share, P); break;
-	case 5: rc = launch_fill<16, 10>(this, n_items, dir, share, P); break;
-	case 6: rc = launch_fill<32, 8>(this, n_items, dir, share, P); break;
-	case 7: rc = launch_fill<32, 10>(this, n_items, dir, share, P); break;
+	case 4: rc = launch_fill<8, 16>(this, n_items, dir, share, P); break;
+	case 5: rc = launch_fill<8, 20>(this, n_items, dir, share, P); break;
+	case 6: rc = launch_fill<16, 16>(this, n_items, dir, share, P); break;
+	case 7: rc = launch_fill<16, 20>(this, n_items, dir, share, P); break;
 	case 8: rc = launch_fill<32, 16>(this, n_items, dir, share, P); break;
-	case 9: rc = launch_fill<8, 20>(this, n_items, dir, share, P); break;
-	case 10: rc = launch_fill<32, 5>(this, n_items, dir, share, P); break;
+	case 9: rc = launch_fill<32, 20>(this, n_items, dir, share, P); break;
+	case 10: rc = launch_fill<32, 4>(this, n_items, dir, share, P); break;
+	case 11: rc = launch_fill<32, 5>(this, n_items, dir, share, P); break;
+	case 12: rc = launch_fill<32, 8>(this, n_items, dir, share, P); break;
+	case 13: rc = launch_fill<32, 10>(this, n_items, dir, share, P); break;
+	case 14: rc = launch_fill<16, 10>(this, n_items, dir, share, P); break;
+	case 15: rc = launch_fill<32, 10>(this, n_items, dir, share, P); break;
 	default: break;
 	}
 	tr.lap("  fill: launch");
@@ -197,7 +214,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 {
 	if (!e || !name) return -1;
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
-	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }
+	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }       /* index into kInst */
 	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 3) / 4 * 4 : SSW_STRIP_SUPER; return 0; }
 	if (!strcmp(name, "mode")) return 0;      /* retired experiment (biased arithmetic with IMAD adds was slower, profiles/fill_kernel_r1.md) */
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
@@ -536,7 +553,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	while (k < pts.size()) {
 		/* one launch = one kernel instance, bounded by the column-maximum budget */
 		const int inst = pts[k].inst;
-		const int per_cta = SSW_FILL_WARPS * (32 / kInst[inst].G);
+		const int per_cta = SSW_FILL_WARPS * (32 / kInst[inst].G);   /* share == 1 launches always use SSW_FILL_WARPS warps */
 		size_t k_end = k, cm_words = 0;
 		int64_t total_cols = 0;
 		while (k_end < pts.size() && pts[k_end].inst == inst) {

@@ -146,11 +146,12 @@ __device__ static __forceinline__ void ssw_load_scores(uint32_t (&s)[R], ssw_sad
 
 /* The R cells of one lane in one column: 5 DPX/ALU instructions per cell pair + 1/2 for the column maximum.
  * In: Hd (H of the previous column, shifted down one row), E, scores, and (inH, inF) from the lane above.
- * Out: Hn (H of this column), updated E and Hd, outH/outF for the lane below, m = max over the lane's rows. */
+ * Out: Hn (H of this column), updated E and Hd, outH/outF/outC for the lane below (outC = maximum of the column
+ * over the rows of this lane and of all lanes above it). */
 template <int R>
 __device__ static __forceinline__ void ssw_cells(uint32_t (&Hd)[R], uint32_t (&E)[R], const uint32_t (&s)[R], uint32_t (&Hn)[R],
-                                                uint32_t inH, uint32_t inF, uint32_t negO, uint32_t negE,
-                                                uint32_t& outH, uint32_t& outF, uint32_t& m)
+                                                uint32_t inH, uint32_t inF, uint32_t inC, uint32_t negO, uint32_t negE,
+                                                uint32_t& outH, uint32_t& outF, uint32_t& outC)
 {
 	uint32_t F = inF;
 #pragma unroll
@@ -161,10 +162,12 @@ __device__ static __forceinline__ void ssw_cells(uint32_t (&Hd)[R], uint32_t (&E
 		Hn[k] = __vmaxs2(X, F);
 		F = __viaddmax_s16x2(F, negE, Xg);
 	}
-	m = 0;
+	/* partial column maximum: the value handed down from the lanes above, folded with this lane's rows */
+	uint32_t m = inC;
 #pragma unroll
 	for (int k = 0; k + 1 < R; k += 2) m = __vimax3_s16x2(m, Hn[k], Hn[k + 1]);
 	if (R & 1) m = __vmaxs2(m, Hn[R - 1]);
+	outC = m;
 	Hd[0] = inH;
 #pragma unroll
 	for (int k = 1; k < R; ++k) Hd[k] = Hn[k - 1];
@@ -172,7 +175,10 @@ __device__ static __forceinline__ void ssw_cells(uint32_t (&Hd)[R], uint32_t (&E
 	outF = F;
 }
 
-/* Running best of one lane: on a strict increase of either half record the scan position and the smallest row. */
+/* Running best of one lane, taken over the partial column maxima it sees (its own rows and all rows above): on a
+ * strict increase of either half it records the scan position and the smallest of ITS rows holding the new value
+ * (none: a large sentinel, the owning lane above records the same position with the real row). */
+#define SSW_NO_ROW 0x3fffffff
 struct SswLaneBest {
 	uint32_t best;
 	int pos0, pos1, row0, row1;
@@ -186,12 +192,12 @@ __device__ static __forceinline__ void ssw_track(SswLaneBest& lb, uint32_t nb, c
 #endif
 	if (sp >= p0 && sp < p1) {
 		if (half_of(nb, 0) > half_of(lb.best, 0)) {
-			lb.pos0 = sp;
+			lb.pos0 = sp; lb.row0 = SSW_NO_ROW;
 #pragma unroll
 			for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 0) == half_of(nb, 0)) lb.row0 = row_base + k;
 		}
 		if (half_of(nb, 1) > half_of(lb.best, 1)) {
-			lb.pos1 = sp;
+			lb.pos1 = sp; lb.row1 = SSW_NO_ROW;
 #pragma unroll
 			for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 1) == half_of(nb, 1)) lb.row1 = row_base + k;
 		}
@@ -219,8 +225,11 @@ __device__ static __forceinline__ void ssw_reduce_best(const SswLaneBest& lb, in
 /* single-strip kernel                                                                                          */
 /* ---------------------------------------------------------------------------------------------------------- */
 
+#ifndef SSW_FILL_MINB
+#define SSW_FILL_MINB 1                     /* minimum resident CTAs per SM asked of ptxas (register cap) */
+#endif
 template <int G, int R, int DIR, bool WRITE_CM, bool TERM>
-__global__ void __launch_bounds__(SSW_FILL_THREADS)
+__global__ void __launch_bounds__(SSW_FILL_THREADS, SSW_FILL_MINB)
 ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
                 const int8_t* __restrict__ mat, int n, int gapO, int gapE,
@@ -240,7 +249,8 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	 * every warp (built cooperatively); otherwise each warp keeps the profile(s) of its own groups */
 	uint32_t* prof = share ? smem : smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
 
-	const int item_idx = ((int)blockIdx.x * SSW_FILL_WARPS + warp) * GPW + g;
+	const int nwarps = (int)(blockDim.x >> 5);           /* SSW_FILL_WARPS, fewer when per-warp profiles are large */
+	const int item_idx = ((int)blockIdx.x * nwarps + warp) * GPW + g;
 	const bool live = item_idx < n_items;
 	SswItem it;
 	if (live) it = items[item_idx];
@@ -250,8 +260,8 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	}
 
 	if (share) {
-		const SswItem& first = items[(int)blockIdx.x * SSW_FILL_WARPS * GPW];     /* always a live item */
-		ssw_build_profile<R>(prof, lane, t * R, first.qa, first.qb, qcodes, mat, n, warp, SSW_FILL_WARPS);
+		const SswItem& first = items[(int)blockIdx.x * nwarps * GPW];               /* always a live item */
+		ssw_build_profile<R>(prof, lane, t * R, first.qa, first.qb, qcodes, mat, n, warp, nwarps);
 		__syncthreads();
 	} else {
 		ssw_build_profile<R>(prof, lane, t * R, it.qa, it.qb, qcodes, mat, n);
@@ -262,13 +272,14 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	const uint8_t* rp = reinterpret_cast<const uint8_t*>(refs) + it.ref_off;   /* reference column 0 */
 	const uint32_t negO = pack2(-gapO, -gapO), negE = pack2(-gapE, -gapE);
 	int sL = (it.p0 - it.warm - (G - 1)) & ~3;          /* scan position of the group's last lane, multiple of 4 */
-	int n_body = live && it.p1 > sL ? (it.p1 - sL + 3) / 4 : 0;
+	constexpr int U = 8;                                /* scan positions per loop body */
+	int n_body = live && it.p1 > sL ? (it.p1 - sL + U - 1) / U : 0;
 #pragma unroll
 	for (int off = G; off < 32; off <<= 1) n_body = max(n_body, __shfl_xor_sync(FULL, n_body, off));
 
 	/* column cursor of this lane for step j = 0 of the current body, clamped into the padded array */
 	int col = DIR > 0 ? sL + (G - 1 - t) : it.cend - (sL + (G - 1 - t));
-	const int col_hi = it.ref_len + SSW_REF_PAD - 4, col_lo = -SSW_REF_PAD + 3;
+	const int col_hi = it.ref_len + SSW_REF_PAD - U, col_lo = -SSW_REF_PAD + U - 1;
 	if (DIR > 0) col = min(col, col_hi); else col = max(col, col_lo);
 	int sp0 = sL + (G - 1 - t);                         /* this lane's scan position at step j = 0 */
 
@@ -289,10 +300,10 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
 
 	for (int body = 0; body < n_body; ++body) {
-		uint32_t cmv[4];
-		const bool maybe_counted = sp0 + 3 >= it.p0 && sp0 < it.p1;   /* this body touches the counted range */
+		uint32_t cmv[U];
+		const bool maybe_counted = sp0 + U - 1 >= it.p0 && sp0 < it.p1;   /* this body touches the counted range */
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
+		for (int j = 0; j < U; ++j) {
 			/* values crossing the lane boundary */
 			const uint32_t inH = __shfl_up_sync(FULL, outH, 1, G) * top_keep;
 			const uint32_t inF = __shfl_up_sync(FULL, outF, 1, G) * top_keep;
@@ -301,36 +312,39 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 			/* reference letter of this lane's scan position and its profile rows */
 			int letter = (int)lptr[DIR * j];
 			if (DIR < 0) { if (sp0 + j < 0) letter = n; }
-			uint32_t s[R], Hn[R], m;
+			uint32_t s[R], Hn[R];
 			ssw_load_scores<R>(s, pbase, ptail, letter);
-			ssw_cells<R>(Hd, E, s, Hn, inH, inF, negO, negE, outH, outF, m);
-			outC = __vmaxs2(inC, m);
+			ssw_cells<R>(Hd, E, s, Hn, inH, inF, inC, negO, negE, outH, outF, outC);
 			cmv[j] = outC;
 
 			/* running best of this lane (strict increase only; rare path) */
-			const uint32_t nb = __vmaxs2(lb.best, m);
+			const uint32_t nb = __vmaxs2(lb.best, outC);
 			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, nb, Hn, sp0 + j, it.p0, it.p1, t * R);
 		}
 
 		if (WRITE_CM) {
-			if (t == G - 1 && sL >= it.p0 && sL < it.p1 && it.cm_off >= 0)
-				*reinterpret_cast<uint4*>(colmax + it.cm_off + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
+			if (t == G - 1 && it.cm_off >= 0) {
+#pragma unroll
+				for (int q = 0; q < U; q += 4)
+					if (sL + q >= it.p0 && sL + q < it.p1)
+						*reinterpret_cast<uint4*>(colmax + it.cm_off + sL + q) = make_uint4(cmv[q], cmv[q + 1], cmv[q + 2], cmv[q + 3]);
+			}
 		}
 		if (TERM) {
 			/* reverse pass: stop after the first column whose maximum equals score1 (ssw.c:339/:541) */
 			int hit = 0;
 			if (t == G - 1 && it.term_a >= 0) {
 #pragma unroll
-				for (int j = 0; j < 4; ++j)
+				for (int j = 0; j < U; ++j)
 					if (sL + j >= it.p0 && sL + j < it.p1 && half_of(cmv[j], 0) == it.term_a) hit = 1;
 			}
 			if (__any_sync(FULL, hit)) break;
 		}
 
-		sL += 4;
-		sp0 += 4;
+		sL += U;
+		sp0 += U;
 		{
-			const int ncol = DIR > 0 ? min(col + 4, col_hi) : max(col - 4, col_lo);
+			const int ncol = DIR > 0 ? min(col + U, col_hi) : max(col - U, col_lo);
 			lptr += ncol - col;
 			col = ncol;
 		}
@@ -491,12 +505,11 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 					if (lane == 0) { inH = bHv[j]; inF = bFv[j]; inC = bCv[j]; }
 					int letter = (int)lptr[DIR * j];
 					if (sp0 + j < 0) letter = n;                    /* before the scan start (reverse: right of cend) */
-					uint32_t sc[R], Hn[R], m;
+					uint32_t sc[R], Hn[R];
 					ssw_load_scores<R>(sc, pbase, ptail, letter);
-					ssw_cells<R>(Hd, E, sc, Hn, inH, inF, negO, negE, outH, outF, m);
-					outC = __vmaxs2(inC, m);
+					ssw_cells<R>(Hd, E, sc, Hn, inH, inF, inC, negO, negE, outH, outF, outC);
 					cmv[j] = outC; hv[j] = outH; fv[j] = outF;
-					const uint32_t nb = __vmaxs2(lb.best, m);
+					const uint32_t nb = __vmaxs2(lb.best, outC);
 					if (nb != lb.best && maybe_counted) ssw_track<R>(lb, nb, Hn, sp0 + j, 0, T.p1, s * 32 * R + lane * R);
 				}
 				/* the last lane publishes the strip's bottom row (the last strip: the column maxima) */
