@@ -175,34 +175,75 @@ __device__ static __forceinline__ void ssw_cells(uint32_t (&Hd)[R], uint32_t (&E
 	outF = F;
 }
 
-/* Running best of one lane, taken over the partial column maxima it sees (its own rows and all rows above): on a
- * strict increase of either half it records the scan position and the smallest of ITS rows holding the new value
- * (none: a large sentinel, the owning lane above records the same position with the real row). */
+/* Running best of one lane, taken over the partial column maxima it sees (its own rows and all rows above).  On a
+ * strict increase of either half the lane records the scan position and parks the column's H values of its rows in
+ * a per-thread snapshot (local memory: a handful of vector stores).  The row -- the smallest of ITS rows holding the
+ * final best value, or a large sentinel when the value came from a lane above, which then records the same position
+ * with the real row -- is looked up in the snapshot once, when the item is finished.  This keeps the event cheap:
+ * with lenient gap penalties (BLOSUM50 with 3/1) the running maximum grows along the whole matrix and events are
+ * frequent. */
 #define SSW_NO_ROW 0x3fffffff
 struct SswLaneBest {
 	uint32_t best;
 	int pos0, pos1, row0, row1;
 };
+template <int R>
+struct SswSnap {
+	uint32_t w[2][R + (4 - R % 4) % 4];
+};
+template <int R>
+__device__ static __forceinline__ void ssw_snap_pin(SswSnap<R>& sn)
+{
+#ifndef SSW_CPU_EMU
+	asm volatile("" : : "l"(&sn) : "memory");       /* the snapshot must live in memory, not in 2R more registers */
+#endif
+#pragma unroll
+	for (int k = 0; k < R; ++k) { sn.w[0][k] = 0; sn.w[1][k] = 0; }
+}
 
 template <int R>
-__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1, int row_base)
+__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, SswSnap<R>& sn, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1,
+                                                uint32_t floor2)
 {
 #ifndef SSW_CPU_EMU
 	asm volatile("" : "+r"(sp));                /* keep the range test inside this rare path */
 #endif
 	if (sp >= p0 && sp < p1) {
-		if (half_of(nb, 0) > half_of(lb.best, 0)) {
-			lb.pos0 = sp; lb.row0 = SSW_NO_ROW;
+		/* `floor2` is a lower bound of the group's final maximum (the group maximum of a few steps ago): an increase
+		 * that stays below it can never be the best cell, so it need not be recorded */
+		if (half_of(nb, 0) > half_of(lb.best, 0) && half_of(nb, 0) >= half_of(floor2, 0)) {
+			lb.pos0 = sp;
 #pragma unroll
-			for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 0) == half_of(nb, 0)) lb.row0 = row_base + k;
+			for (int k = 0; k < R; ++k) sn.w[0][k] = Hn[k];
 		}
-		if (half_of(nb, 1) > half_of(lb.best, 1)) {
-			lb.pos1 = sp; lb.row1 = SSW_NO_ROW;
+		if (half_of(nb, 1) > half_of(lb.best, 1) && half_of(nb, 1) >= half_of(floor2, 1)) {
+			lb.pos1 = sp;
 #pragma unroll
-			for (int k = R - 1; k >= 0; --k) if (half_of(Hn[k], 1) == half_of(nb, 1)) lb.row1 = row_base + k;
+			for (int k = 0; k < R; ++k) sn.w[1][k] = Hn[k];
 		}
 		lb.best = nb;
 	}
+}
+
+/* after the sweep: smallest row of this lane that held the lane's best value when it was recorded */
+template <int R>
+__device__ static __forceinline__ void ssw_track_rows(SswLaneBest& lb, const SswSnap<R>& sn, int row_base)
+{
+	lb.row0 = SSW_NO_ROW; lb.row1 = SSW_NO_ROW;
+#pragma unroll
+	for (int k = R - 1; k >= 0; --k) {
+		if (half_of(sn.w[0][k], 0) == half_of(lb.best, 0)) lb.row0 = row_base + k;
+		if (half_of(sn.w[1][k], 1) == half_of(lb.best, 1)) lb.row1 = row_base + k;
+	}
+}
+
+/* maximum of `v` (packed s16x2) over the lanes of a group */
+template <int G>
+__device__ static __forceinline__ uint32_t ssw_group_max(uint32_t v)
+{
+#pragma unroll
+	for (int off = G / 2; off >= 1; off >>= 1) v = __vmaxs2(v, __shfl_xor_sync(0xffffffffu, v, off, G));
+	return v;
 }
 
 /* Reduce the lanes of a group to one record per half: max score, then first position, then smallest row. */
@@ -298,9 +339,13 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	uint32_t outH = 0, outF = 0, outC = 0;
 	SswLaneBest lb;
 	lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
+	SswSnap<R> snap;
+	ssw_snap_pin<R>(snap);
 
+	uint32_t floor2 = 0;                                /* lower bound of the group's final maximum, refreshed every 4 bodies */
 	for (int body = 0; body < n_body; ++body) {
 		uint32_t cmv[U];
+		if ((body & 3) == 0) floor2 = ssw_group_max<G>(lb.best);
 		const bool maybe_counted = sp0 + U - 1 >= it.p0 && sp0 < it.p1;   /* this body touches the counted range */
 #pragma unroll
 		for (int j = 0; j < U; ++j) {
@@ -319,7 +364,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 
 			/* running best of this lane (strict increase only; rare path) */
 			const uint32_t nb = __vmaxs2(lb.best, outC);
-			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, nb, Hn, sp0 + j, it.p0, it.p1, t * R);
+			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, it.p0, it.p1, floor2);
 		}
 
 		if (WRITE_CM) {
@@ -350,6 +395,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		}
 	}
 
+	ssw_track_rows<R>(lb, snap, t * R);
 	int sc0, bp0, br0, sc1, bp1, br1;
 	ssw_reduce_best<G>(lb, sc0, bp0, br0, sc1, bp1, br1);
 	if (live && t == 0) {
@@ -460,6 +506,8 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 			}
 			SswLaneBest lb;
 			lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
+			SswSnap<R> snap;
+			ssw_snap_pin<R>(snap);
 
 			const uint32_t* bin = bnd + T.bnd_off + (size_t)((s + 1) & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;   /* written by strip s-1 */
 			uint32_t* bout = bnd + T.bnd_off + (size_t)(s & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;
@@ -510,7 +558,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 					ssw_cells<R>(Hd, E, sc, Hn, inH, inF, inC, negO, negE, outH, outF, outC);
 					cmv[j] = outC; hv[j] = outH; fv[j] = outF;
 					const uint32_t nb = __vmaxs2(lb.best, outC);
-					if (nb != lb.best && maybe_counted) ssw_track<R>(lb, nb, Hn, sp0 + j, 0, T.p1, s * 32 * R + lane * R);
+					if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, 0, T.p1, 0u);
 				}
 				/* the last lane publishes the strip's bottom row (the last strip: the column maxima) */
 				if (lane == 31 && sL >= 0) {
@@ -547,6 +595,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 				for (int k = 0; k < R; ++k) { pk[k] = Hd[k]; pk[R + k] = E[k]; }
 				pk[2 * R] = outH; pk[2 * R + 1] = outF; pk[2 * R + 2] = outC;
 			}
+			ssw_track_rows<R>(lb, snap, s * 32 * R + lane * R);
 			int sc0, bp0, br0, sc1, bp1, br1;
 			ssw_reduce_best<32>(lb, sc0, bp0, br0, sc1, bp1, br1);
 			if (lane == 0) {
