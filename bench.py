@@ -173,6 +173,10 @@ def main():
     import common as C
     from __graft_entry__ import load_package
     L = load_package()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ssw_b200_dist", os.path.join(ROOT, "complete-striped-smith-waterman-library_b200", "ssw_dist.py"))
+    D = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(D)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,12 +207,8 @@ def main():
         return res
 
     def gather(res):
-        if world == 1:
-            return res
-        t = torch.from_numpy(res.view(np.uint8).copy()).cuda()
-        out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, out, dst=0)
-        return out
+        # fixed-size result records of every rank -> rank 0 (NCCL gather over NVLink), the only collective of a step
+        return D.gather_records(res, rank, world, device="cuda:%d" % local)
 
     # ---- device-resident timing (`value`) ----
     eng.set_sequences(reads, [ref])
