@@ -526,23 +526,51 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	}
 	if (keys.empty()) return 0;
 
-	/* ---- queries of one strip: pair-tasks = two alignments on the same reference ---- */
-	std::sort(keys.begin(), keys.end(), by_ref);
+	/* ---- queries of one strip: pair-tasks = two alignments on the same reference ----
+	 * Ordering is done with counting sorts (O(pairs)): a comparison sort of millions of keys costs more than the
+	 * kernels for large grids.  rank[q] orders the distinct queries by (instance, padded length, id). */
 	struct PT { int inst; int64_t a, b; int32_t r, qa, qb; };
 	std::vector<PT> pts;
-	for (size_t i = 0; i < keys.size();) {
-		PT pt; pt.inst = keys[i].inst; pt.a = keys[i].idx; pt.b = -1; pt.r = keys[i].r; pt.qa = keys[i].q; pt.qb = -1;
-		++i;
-		if (i < keys.size() && keys[i].inst == pt.inst && keys[i].r == pt.r) { pt.b = keys[i].idx; pt.qb = keys[i].q; ++i; }
-		pts.push_back(pt);
+	{
+		std::vector<int32_t> qids;
+		qids.reserve(keys.size());
+		std::vector<int32_t> rank((size_t)e->n_q, -1), q_inst((size_t)e->n_q, 0);
+		for (const Key& k : keys) if (rank[k.q] < 0) { rank[k.q] = 0; q_inst[k.q] = k.inst; qids.push_back(k.q); }
+		std::sort(qids.begin(), qids.end(), [&](int32_t x, int32_t y) {
+			if (q_inst[x] != q_inst[y]) return q_inst[x] < q_inst[y];
+			const int lx = lp_of((int)(e->q_off[x + 1] - e->q_off[x]), word), ly = lp_of((int)(e->q_off[y + 1] - e->q_off[y]), word);
+			return lx != ly ? lx < ly : x < y;
+		});
+		for (size_t i = 0; i < qids.size(); ++i) rank[qids[i]] = (int32_t)i;
+		const size_t nq = qids.size();
+		/* stable LSD: by rank, then by reference */
+		std::vector<uint32_t> cnt(std::max<size_t>(nq, (size_t)e->n_r) + 1);
+		std::vector<Key> tmp(keys.size());
+		std::fill(cnt.begin(), cnt.end(), 0u);
+		for (const Key& k : keys) ++cnt[(size_t)rank[k.q] + 1];
+		for (size_t i = 1; i <= nq; ++i) cnt[i] += cnt[i - 1];
+		for (const Key& k : keys) tmp[cnt[rank[k.q]]++] = k;
+		std::fill(cnt.begin(), cnt.end(), 0u);
+		for (const Key& k : tmp) ++cnt[(size_t)k.r + 1];
+		for (size_t i = 1; i <= (size_t)e->n_r; ++i) cnt[i] += cnt[i - 1];
+		for (const Key& k : tmp) keys[cnt[k.r]++] = k;
+		/* keys are now ordered by (reference, instance, padded length, query): pair neighbours */
+		pts.reserve(keys.size() / 2 + 1);
+		for (size_t i = 0; i < keys.size();) {
+			PT pt; pt.inst = keys[i].inst; pt.a = keys[i].idx; pt.b = -1; pt.r = keys[i].r; pt.qa = keys[i].q; pt.qb = -1;
+			++i;
+			if (i < keys.size() && keys[i].inst == pt.inst && keys[i].r == pt.r) { pt.b = keys[i].idx; pt.qb = keys[i].q; ++i; }
+			pts.push_back(pt);
+		}
+		/* query-pair major order (stable by rank of the first query; references stay ascending): consecutive items
+		 * then share their two queries, so a CTA needs one profile */
+		std::vector<PT> ptmp(pts.size());
+		std::fill(cnt.begin(), cnt.end(), 0u);
+		for (const PT& t : pts) ++cnt[(size_t)rank[t.qa] + 1];
+		for (size_t i = 1; i <= nq; ++i) cnt[i] += cnt[i - 1];
+		for (const PT& t : pts) ptmp[cnt[rank[t.qa]]++] = t;
+		pts.swap(ptmp);
 	}
-	/* query-pair major order: consecutive items then share their two queries, so a CTA needs one profile */
-	std::sort(pts.begin(), pts.end(), [](const PT& x, const PT& y) {
-		if (x.inst != y.inst) return x.inst < y.inst;
-		if (x.qa != y.qa) return x.qa < y.qa;
-		if (x.qb != y.qb) return x.qb < y.qb;
-		return x.r < y.r;
-	});
 	tr.lap("forward: sort");
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);

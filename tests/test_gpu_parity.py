@@ -209,6 +209,35 @@ def test_word_saturation_and_linear_gaps(ours, engine, checker, capfd):
             assert C.diff_results(batch_dict(res, pool, i), exp) == [], (gapO, gapE, i)
 
 
+@pytest.mark.parametrize("score_size,flag", [(2, 0), (2, 0x0f), (1, 9), (0, 1)])
+def test_ragged_grid_batch(engine, checker, score_size, flag, capfd):
+    """A queries x references grid with ragged lengths (1..1,300 rows, 40..4,000 columns) through the batch ABI:
+    exercises pair-task formation, CTA-shared and per-warp profiles, every kernel instance, the strip kernel,
+    word-first prediction, byte<->word re-resolve / re-fill, NULL results (score_size 0 overflow)."""
+    rng = np.random.default_rng(777 + score_size * 16 + flag)
+    mat = C.dna_matrix(2, 2)
+    refs = [rng.integers(0, 4, size=int(n)).astype(np.int8) for n in (40, 333, 1000, 2048, 4000, 77, 512)]
+    queries = []
+    for i in range(96):
+        n = int(rng.choice([1, 7, 15, 16, 17, 31, 33, 40, 64, 65, 100, 128, 150, 151, 160, 161, 250, 256, 300, 320, 333, 500, 512, 513, 700, 1300]))
+        r = refs[int(rng.integers(0, len(refs)))]
+        if len(r) > n + 10 and rng.random() < 0.7:
+            queries.append(C.mutate_read(rng, r, int(rng.integers(0, len(r) - n - 5)), n, 0.06 if n > 128 else 0.12, 0.01, 0.01))
+        else:
+            queries.append(rng.integers(0, 4, size=n).astype(np.int8))
+    engine.set_sequences(queries, refs)
+    res, pool = engine.align(mat, 5, 3, 1, flag=flag, filters=20, filterd=32767, mask_len=-1, score_size=score_size)
+    k = 0
+    for q in queries:
+        for r in refs:
+            exp = checker.align(q, r, mat, 5, 3, 1, flag, 20, 32767, len(q) // 2, score_size)
+            if exp is None:
+                assert int(res[k]["status"]) == 1, (k, len(q), len(r))
+            else:
+                assert int(res[k]["status"]) == 0 and C.diff_results(batch_dict(res, pool, k), exp) == [], (k, len(q), len(r))
+            k += 1
+
+
 def test_edge_cases(ours, checker, capfd):
     """Length-1 sequences, all-N queries, zero score, maskLen < 15, ragged batch."""
     mat = C.dna_matrix(2, 2)
