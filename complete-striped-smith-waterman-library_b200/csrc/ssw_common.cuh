@@ -50,6 +50,13 @@ static inline void ssw_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 #endif
 }
 
+/* spin-wait pause: the emulator's fibers are cooperative, so a waiting thread must yield */
+#ifdef SSW_CPU_EMU
+#define SSW_SPIN_PAUSE() cuemu::yield_now()
+#else
+#define SSW_SPIN_PAUSE() __nanosleep(64)
+#endif
+
 /* ---- geometry constants ---------------------------------------------------- */
 #define SSW_REF_PAD 64          /* null letters stored before and after every reference */
 #define SSW_NEG16 (-32768)      /* score of dead rows / null letters: keeps H at exactly 0 */

@@ -216,6 +216,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }       /* index into kInst */
 	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 3) / 4 * 4 : SSW_STRIP_SUPER; return 0; }
+	if (!strcmp(name, "tb_maxbw")) { g_ssw_tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
 	if (!strcmp(name, "mode")) return 0;      /* retired experiment (biased arithmetic with IMAD adds was slower, profiles/fill_kernel_r1.md) */
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;

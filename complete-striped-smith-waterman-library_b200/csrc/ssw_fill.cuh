@@ -442,10 +442,8 @@ struct SswStripTask {
 
 #ifdef SSW_CPU_EMU
 template <class T> __device__ static __forceinline__ T ssw_ldcg(const T* p) { return *p; }
-#define SSW_SPIN_PAUSE() cuemu::yield_now()          /* cooperative fibers: let the producer run */
 #else
 template <class T> __device__ static __forceinline__ T ssw_ldcg(const T* p) { return __ldcg(p); }
-#define SSW_SPIN_PAUSE() __nanosleep(64)
 #endif
 
 template <int R, int DIR, bool TERM>

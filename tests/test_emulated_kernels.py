@@ -70,7 +70,8 @@ def test_emulated_chunked_reference(oracle, capfd):
     reads = [C.mutate_read(rng, ref, int(rng.integers(0, 1400)), int(rng.integers(20, 41)), 0.1, 0.02, 0.02) for _ in range(7)]
     reads.append(rng.integers(0, 4, size=33).astype(np.int8))
     eng.set_sequences(reads, [ref])
-    for flag in (0, 0x0f):
+    for flag in (0, 0x0f, 1):
+        eng.set_option("tb_maxbw", 0 if flag == 1 else -1)      # flag 1: the single-warp traceback kernel
         res, pool = eng.align(mat, 5, 3, 2, flag=flag, filterd=32767, mask_len=15, score_size=2)
         for i, q in enumerate(reads):
             exp = oracle.align(q, ref, mat, 5, 3, 2, flag, 0, 32767, 15, 2)
@@ -78,6 +79,7 @@ def test_emulated_chunked_reference(oracle, capfd):
             got = {k: int(r[k]) for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
             got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
             assert C.diff_results(got, exp) == [], (flag, i)
+    eng.set_option("tb_maxbw", -1)
     eng.close()
 
 
