@@ -53,8 +53,10 @@ static inline void ssw_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 /* spin-wait pause: the emulator's fibers are cooperative, so a waiting thread must yield */
 #ifdef SSW_CPU_EMU
 #define SSW_SPIN_PAUSE() cuemu::yield_now()
+#define SSW_SPIN_TIGHT() cuemu::yield_now()
 #else
-#define SSW_SPIN_PAUSE() __nanosleep(64)
+#define SSW_SPIN_PAUSE() __nanosleep(64)     /* waits that are rarely entered (strip pipeline: the producer runs ahead) */
+#define SSW_SPIN_TIGHT() ((void)0)           /* hand-offs on the critical path (traceback rows): a sleep would cost ~1 us per row */
 #endif
 
 /* ---- geometry constants ---------------------------------------------------- */

@@ -3,7 +3,8 @@
  * and CIGAR re-scoring: the follow-up kernel that replaces banded_sw
  * (src/ssw.c:590-783) and cigar_alignment_score (:785-811).
  *
- * One warp per alignment.  The band of query row i covers reference columns
+ * One warp per alignment (two kernels: rows in shared memory for bands up to
+ * SSW_TBP_MAXBW, rows in global memory beyond).  The band of query row i covers reference columns
  * [max(0,i-bw), min(refLen-1,i+bw)] (ssw.c:630-632).  A row is processed 32
  * columns at a time: E and the diagonal term depend only on the previous row;
  * the in-row gap F obeys  F(j+1) = max(Y(j) - gapO, F(j) - min(gapO,gapE))
@@ -52,6 +53,7 @@ struct SswTbTask {
 	int64_t dir_off;     /* byte offset of this task's direction cells in the scratch */
 	int64_t row_off;     /* int32 offset of this task's 4 row buffers */
 	int64_t cig_off;     /* word offset of this task's CIGAR buffer */
+	int64_t dbg_fill, dbg_walk, dbg_score;   /* clock64 deltas of the last round (diagnostics, SSW_TRACE) */
 };
 
 __device__ static __forceinline__ uint32_t ssw_tb_pack(uint32_t len, uint32_t op) { return (len << 4) | op; }  /* op: M0 I1 D2 */
@@ -109,124 +111,207 @@ __device__ static void ssw_tb_finish(SswTbTask& T, SswTbTask* slot, const int8_t
 	*slot = T;
 }
 
-/*
- * Row-pipelined variant (bands up to SSW_TBP_MAXBW): one CTA per alignment, its warps take the query rows round
- * robin; row i starts a tile as soon as row i-1 has finished the same 32-column tile.  The H and E rows live in a
- * ring of shared-memory row slots (one more slot than warps, so a slot is only reused after its reader is done),
- * indexed by reference column modulo the ring width.  Cell arithmetic, quirks and outputs are those of the
- * single-warp kernel below.
- */
-#define SSW_TBP_WARPS 4
-#define SSW_TBP_SLOTS (SSW_TBP_WARPS + 1)
-#define SSW_TBP_MAXBW 990
-static int g_ssw_tb_maxbw = SSW_TBP_MAXBW;           /* "tb_maxbw" option: bands above this use the single-warp kernel (tests: 0) */
+/* One 32-column tile of one band row: E and the diagonal term from the previous row, F by a warp max-plus scan
+ * with the carries of the tile to the left, H, and the direction byte.  Shared by both banded kernels. */
+__device__ static __forceinline__ void ssw_tb_tile(bool act, int i, int j, int beg, int lane, int Hup, int Eup, int Hdg, int s,
+                                                  int gapO, int gapE, int g, int& carryF, int& carryH, int& carryFp,
+                                                  int& Hv, int& Ev, int& dirb)
+{
+	constexpr unsigned FULL = 0xffffffffu;
+	const int t1 = i == 0 ? -gapO : Hup - gapO;
+	const int t2 = i == 0 ? SSW_TB_NEGINF : Eup - gapE;
+	Ev = t1 > t2 ? t1 : t2;
+	const int de3 = t1 > t2 ? 1 : 0;
+	const int e1 = Ev > 0 ? Ev : 0;
+	const int T2 = Hdg + s;
+	const int Y = e1 > T2 ? e1 : T2;
+	/* in-row gap: inclusive max-plus scan of A = Y - gapO with decay g per column */
+	int P = act ? Y - gapO : SSW_TB_NEGINF;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int o = __shfl_up_sync(FULL, P, d);
+		if (lane >= d) P = max(P, o - d * g);
+	}
+	const int Pm1 = __shfl_up_sync(FULL, P, 1);
+	const int Fv = lane == 0 ? carryF : max(Pm1, carryF - lane * g);
+	Hv = Y > Fv ? Y : Fv;
+	/* df from the left neighbour's H and F */
+	int Hl = __shfl_up_sync(FULL, Hv, 1), Fl = __shfl_up_sync(FULL, Fv, 1);
+	if (lane == 0) { Hl = carryH; Fl = carryFp; }
+	const int df5 = j == beg ? 1 : ((Hl - gapO > Fl - gapE) ? 1 : 0);       /* j == beg: 0 - gapO > neg_inf - gapE */
+	const int f1 = Fv > 0 ? Fv : 0;
+	const int T1 = e1 > f1 ? e1 : f1;
+	const int hsel = T1 <= T2 ? 0 : (e1 > f1 ? 1 : 2);
+	dirb = de3 | (df5 << 1) | (hsel << 2);
+	/* carries into the next tile */
+	const int P31 = __shfl_sync(FULL, P, 31);
+	carryH = __shfl_sync(FULL, Hv, 31);
+	carryFp = __shfl_sync(FULL, Fv, 31);
+	carryF = max(P31, carryF - 32 * g);
+}
 
-__global__ void __launch_bounds__(SSW_TBP_WARPS * 32)
-ssw_banded_rows_kernel(SswTbTask* __restrict__ tasks,
+/*
+ * Fast variant for bands up to SSW_TBP_MAXBW: one warp per alignment, four alignments per CTA.  The two live H/E
+ * rows sit in shared memory (indexed by reference column modulo the ring width), the scoring matrix too, so a
+ * tile's critical path has no global-memory latency.  After the fill the warp stages blocks of direction bytes into
+ * its (now free) row memory with coalesced loads and lane 0 walks the traceback inside them: the plain walk pays a
+ * DRAM latency per step because every step moves up one band row.
+ */
+#define SSW_TBP_MAXBW 990
+static int g_ssw_tb_maxbw = SSW_TBP_MAXBW;           /* "tb_maxbw" option: bands above this use the global-memory kernel (tests: 0) */
+
+__global__ void __launch_bounds__(SSW_TB_THREADS)
+ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
                        const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
                        const int8_t* __restrict__ mat, int n, int gapO, int gapE,
                        uint8_t* __restrict__ dir_base, uint32_t* __restrict__ cig_base, int ring)
 {
 	constexpr unsigned FULL = 0xffffffffu;
-	SSW_DYN_SMEM(int32_t, rows);                                  /* [slot][H|E][ring] */
-	__shared__ volatile int p_row[SSW_TBP_SLOTS], p_tile[SSW_TBP_SLOTS];
-	__shared__ int red_v[SSW_TBP_WARPS], red_i[SSW_TBP_WARPS], red_j[SSW_TBP_WARPS];
+	SSW_DYN_SMEM(int32_t, smem);                                  /* [warp][4][ring] ints, then n*n matrix bytes */
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	SswTbTask T = tasks[blockIdx.x];
+	int8_t* smat = reinterpret_cast<int8_t*>(smem + (size_t)SSW_TB_WARPS * 4 * ring);
+	for (int k = threadIdx.x; k < n * n; k += blockDim.x) smat[k] = mat[k];
+	__syncthreads();
+	const int ti = (int)blockIdx.x * SSW_TB_WARPS + warp;
+	if (ti >= n_tasks) return;
+	SswTbTask T = tasks[ti];
 	const int8_t* ref = refs + T.ref_off;
 	const int8_t* read = qcodes + T.read_off;
-	const int rl = T.ref_len, ql = T.read_len, bw = T.bw;
-	const int W = 2 * bw + 1, mask = ring - 1;
+	const int rl = T.ref_len, ql = T.read_len;
+	const int mask = ring - 1;
 	const int g = gapO < gapE ? gapO : gapE;
 	uint8_t* dir = dir_base + T.dir_off + 1;
-	if (threadIdx.x < SSW_TBP_SLOTS) { p_row[threadIdx.x] = -1; p_tile[threadIdx.x] = 0; }
-	__syncthreads();
+	int32_t* mine = smem + (size_t)warp * 4 * ring;
+	int32_t* Hrow[2] = {mine, mine + ring};
+	int32_t* Erow[2] = {mine + 2 * ring, mine + 3 * ring};
+	const int len = rl > ql ? rl : ql;
+	const long long c0 = clock64();
+	int bw = T.bw, W = 2 * bw + 1;
 
-	int bestv = 0, besti = 0, bestj = 0;
-	for (int i = warp; i < ql; i += SSW_TBP_WARPS) {
-		const int slot = i % SSW_TBP_SLOTS, pslot = (i + SSW_TBP_SLOTS - 1) % SSW_TBP_SLOTS;
-		int32_t* Hc = rows + (size_t)slot * 2 * ring;
-		int32_t* Ec = Hc + ring;
-		const int32_t* Hp = rows + (size_t)pslot * 2 * ring;
-		const int32_t* Ep = Hp + ring;
-		const int beg = max(0, i - bw), end = min(rl - 1, i + bw);
-		const int pbeg = max(0, i - 1 - bw);
-		const bool top_oob = (i <= bw + 1) || (end == i + bw);
-		const int rd = (int)read[i];
-		uint8_t* drow = dir + (size_t)W * i - beg;
-		if (lane == 0) { p_tile[slot] = beg >> 5; __threadfence_block(); p_row[slot] = i; }
-		int carryF = -gapO + (beg & 31) * g;                      /* gives F(beg) = -gapO at the first active lane */
-		int carryH = 0, carryFp = 0;
-		for (int kt = beg >> 5; kt <= (end >> 5); ++kt) {
-			const int j = kt * 32 + lane;
-			const bool act = j >= beg && j <= end;
-			if (i > 0) {
-				if (lane == 0) { while (!(p_row[pslot] == i - 1 && p_tile[pslot] > kt)) { SSW_SPIN_PAUSE(); } }
-				__syncwarp();
-			}
-			int Hup = 0, Eup = SSW_TB_NEGINF, Hdg = 0, s = 0;
-			if (act) {
-				if (i > 0) {
-					if (!(j == end && top_oob)) { Hup = Hp[j & mask]; Eup = Ep[j & mask]; }
-					if (j - 1 >= pbeg) Hdg = Hp[(j - 1) & mask];
+	/* band-doubling loop of banded_sw (ssw.c:616-680), kept inside the kernel while the doubled band still fits the
+	 * row ring: only the last band's directions are needed, and the running maximum is carried in T */
+	for (;;) {
+		W = 2 * bw + 1;
+		int bestv = 0, besti = 0, bestj = 0;
+		int rd_next = (int)read[0];
+		for (int i = 0; i < ql; ++i) {
+			const int cur = i & 1, prv = cur ^ 1;
+			const int beg = max(0, i - bw), end = min(rl - 1, i + bw);
+			const int pbeg = max(0, i - 1 - bw);
+			const bool top_oob = (i <= bw + 1) || (end == i + bw);
+			const int rd = rd_next;
+			if (i + 1 < ql) rd_next = (int)read[i + 1];
+			uint8_t* drow = dir + (size_t)W * i - beg;
+			{
+				int carryF = -gapO, carryH = 0, carryFp = 0;
+				for (int j0 = beg; j0 <= end; j0 += 32) {
+					const int j = j0 + lane;
+					const bool act = j <= end;
+					int Hup = 0, Eup = SSW_TB_NEGINF, Hdg = 0, s = 0;
+					if (act) {
+						if (i > 0) {
+							if (!(j == end && top_oob)) { Hup = Hrow[prv][j & mask]; Eup = Erow[prv][j & mask]; }
+							if (j - 1 >= pbeg) Hdg = Hrow[prv][(j - 1) & mask];
+						}
+						s = (int)smat[(int)ref[j] * n + rd];
+					}
+					int Hv, Ev, dirb;
+					ssw_tb_tile(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryH, carryFp, Hv, Ev, dirb);
+					if (act) {
+						Hrow[cur][j & mask] = Hv;
+						Erow[cur][j & mask] = Ev;
+						drow[j] = (uint8_t)dirb;
+						if (Hv > bestv) { bestv = Hv; besti = i; bestj = j; }
+					}
 				}
-				s = (int)mat[(int)ref[j] * n + rd];
 			}
-			const int t1 = i == 0 ? -gapO : Hup - gapO;
-			const int t2 = i == 0 ? SSW_TB_NEGINF : Eup - gapE;
-			const int Ev = t1 > t2 ? t1 : t2;
-			const int de3 = t1 > t2 ? 1 : 0;
-			const int e1 = Ev > 0 ? Ev : 0;
-			const int T2 = Hdg + s;
-			const int Y = e1 > T2 ? e1 : T2;
-			int P = act ? Y - gapO : SSW_TB_NEGINF;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const int o = __shfl_up_sync(FULL, P, d);
-				if (lane >= d) P = max(P, o - d * g);
-			}
-			const int Pm1 = __shfl_up_sync(FULL, P, 1);
-			const int Fv = lane == 0 ? carryF : max(Pm1, carryF - lane * g);
-			const int Hv = Y > Fv ? Y : Fv;
-			int Hl = __shfl_up_sync(FULL, Hv, 1), Fl = __shfl_up_sync(FULL, Fv, 1);
-			if (lane == 0) { Hl = carryH; Fl = carryFp; }
-			const int df5 = j == beg ? 1 : ((Hl - gapO > Fl - gapE) ? 1 : 0);
-			const int f1 = Fv > 0 ? Fv : 0;
-			const int T1 = e1 > f1 ? e1 : f1;
-			const int hsel = T1 <= T2 ? 0 : (e1 > f1 ? 1 : 2);
-			if (act) {
-				Hc[j & mask] = Hv;
-				Ec[j & mask] = Ev;
-				drow[j] = (uint8_t)(de3 | (df5 << 1) | (hsel << 2));
-				if (Hv > bestv) { bestv = Hv; besti = i; bestj = j; }
-			}
-			const int P31 = __shfl_sync(FULL, P, 31);
-			carryH = __shfl_sync(FULL, Hv, 31);
-			carryFp = __shfl_sync(FULL, Fv, 31);
-			carryF = max(P31, carryF - 32 * g);
 			__syncwarp();
-			if (lane == 0) { __threadfence_block(); p_tile[slot] = kt + 1; }
 		}
-		if (lane == 0) { __threadfence_block(); p_tile[slot] = 0x7fffffff; }
-	}
 #pragma unroll
-	for (int off = 16; off >= 1; off >>= 1) {
-		const int ov = __shfl_xor_sync(FULL, bestv, off), oi = __shfl_xor_sync(FULL, besti, off), oj = __shfl_xor_sync(FULL, bestj, off);
-		if (ov > bestv || (ov == bestv && (oi < besti || (oi == besti && oj < bestj)))) { bestv = ov; besti = oi; bestj = oj; }
+		for (int off = 16; off >= 1; off >>= 1) {
+			const int ov = __shfl_xor_sync(FULL, bestv, off), oi = __shfl_xor_sync(FULL, besti, off), oj = __shfl_xor_sync(FULL, bestj, off);
+			if (ov > bestv || (ov == bestv && (oi < besti || (oi == besti && oj < bestj)))) { bestv = ov; besti = oi; bestj = oj; }
+		}
+		if (bestv > T.max) { T.max = bestv; T.max_i = besti; T.max_j = bestj; }     /* strict, carried across doublings */
+		if (!(T.max < T.score && 2 * bw <= len)) break;                              /* ssw.c:678-679: done */
+		if (2 * (2 * bw) + 66 > ring) {                                              /* the next band needs a wider ring: back to the host */
+			T.bw = bw;
+			if (lane == 0) { T.status = SSW_TB_WIDER; tasks[ti] = T; }
+			return;
+		}
+		bw *= 2;
+		__syncwarp();
 	}
-	if (lane == 0) { red_v[warp] = bestv; red_i[warp] = besti; red_j[warp] = bestj; }
+	T.bw = bw;
+	const long long c1 = clock64();
+	T.dbg_fill = c1 - c0; T.dbg_walk = 0; T.dbg_score = 0;
 	__threadfence_block();
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		for (int w = 1; w < SSW_TBP_WARPS; ++w)
-			if (red_v[w] > bestv || (red_v[w] == bestv && (red_i[w] < besti || (red_i[w] == besti && red_j[w] < bestj)))) {
-				bestv = red_v[w]; besti = red_i[w]; bestj = red_j[w];
+	__syncwarp();
+
+	/* ---- traceback (ssw.c:683-762), staged through the warp's row memory ---- */
+	uint32_t* cig = cig_base + T.cig_off;
+	uint8_t* stage = reinterpret_cast<uint8_t*>(mine);
+	const int stage_bytes = 4 * ring * (int)sizeof(int32_t);
+	const long long dir_cells = (long long)W * ql;
+	const int rows_per_block = max(1, (stage_bytes - 8) / W);
+	int wi = T.max_i, wj = T.max_j, e = 0, l = 0, state = 2, op = 0, prev = 0;
+	int bad = 0, more = (wi >= 0 && wj > 0) ? 1 : 0;
+	while (more) {
+		const int i_lo = max(0, wi - rows_per_block + 1);
+		const long long base = (long long)W * i_lo - 1;               /* first staged cell: x == -1 of the lowest row */
+		const long long last = min((long long)W * (wi + 1), dir_cells);   /* last staged cell: x == 2bw+1 of the top row */
+		for (long long c = base + lane; c <= last; c += 32) stage[c - base] = dir[c];
+		__syncwarp();
+		if (lane == 0) {
+			more = 0;
+			while (wi >= 0 && wj > 0) {
+				if (wi < i_lo) { more = 1; break; }
+				const long long cell = (long long)W * wi + (wj - max(wi - bw, 0));
+				if (cell < -1 || cell > dir_cells) { bad = 1; break; }    /* far outside the band: the reference reads unrelated memory */
+				const int b = (cell >= base && cell <= last) ? (int)stage[cell - base] : (int)dir[cell];
+				int code;
+				if (state == 2) { const int hs = (b >> 2) & 3; code = hs == 0 ? 1 : (hs == 1 ? ((b & 1) ? 3 : 2) : (hs == 2 ? ((b & 2) ? 5 : 4) : 0)); }
+				else if (state == 0) code = (b & 1) ? 3 : 2;
+				else code = (b & 2) ? 5 : 4;
+				if (code == 1) { --wi; --wj; state = 2; op = 0; }
+				else if (code == 2) { --wi; state = 0; op = 1; }
+				else if (code == 3) { --wi; state = 2; op = 1; }
+				else if (code == 4) { --wj; state = 1; op = 2; }
+				else if (code == 5) { --wj; state = 2; op = 2; }
+				else { bad = 1; break; }
+				if (op == prev) ++e;
+				else { cig[l++] = ssw_tb_pack((uint32_t)e, (uint32_t)prev); prev = op; e = 1; }
 			}
-		if (bestv > T.max) { T.max = bestv; T.max_i = besti; T.max_j = bestj; }
-		ssw_tb_finish(T, tasks + blockIdx.x, ref, read, mat, n, gapO, gapE, dir, cig_base);
+		}
+		more = __shfl_sync(FULL, more, 0);
+		wi = __shfl_sync(FULL, wi, 0);
+		__syncwarp();
 	}
+	if (lane != 0) return;
+	const long long c2 = clock64();
+	T.dbg_walk = c2 - c1;
+	if (bad) { T.status = SSW_TB_ERROR; T.cig_len = 0; tasks[ti] = T; return; }
+	if (op == 0) cig[l++] = ssw_tb_pack((uint32_t)(e + 1), 0);
+	else { cig[l++] = ssw_tb_pack((uint32_t)e, (uint32_t)op); cig[l++] = ssw_tb_pack(1, 0); }
+	for (int a = 0, b2 = l - 1; a < b2; ++a, --b2) { const uint32_t tmp = cig[a]; cig[a] = cig[b2]; cig[b2] = tmp; }
+	/* ---- CIGAR re-scoring (ssw.c:785-811) ---- */
+	int sc = 0, rp = 0, qp = 0;
+	for (int k = 0; k < l; ++k) {
+		const uint32_t clen = cig[k] >> 4, cop = cig[k] & 15;
+		if (cop == 0) {
+			for (uint32_t x = 0; x < clen; ++x) { sc += (int)smat[(int)ref[rp] * n + (int)read[qp]]; ++rp; ++qp; }
+		} else {
+			sc -= gapO + (clen > 1 ? (int)(clen - 1) * gapE : 0);
+			if (cop == 1) qp += (int)clen; else rp += (int)clen;
+		}
+	}
+	T.cig_len = l;
+	T.status = sc == T.score ? SSW_TB_OK : SSW_TB_MISMATCH;
+	T.dbg_score = clock64() - c2;
+	tasks[ti] = T;
 }
 
+/* General variant (any band width): one warp per alignment, H/E rows in global memory. */
 __global__ void __launch_bounds__(SSW_TB_THREADS)
 ssw_banded_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
                   const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
@@ -269,43 +354,14 @@ ssw_banded_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
 				}
 				s = (int)mat[(int)ref[j] * n + rd];
 			}
-			int t1 = i == 0 ? -gapO : Hup - gapO;
-			int t2 = i == 0 ? SSW_TB_NEGINF : Eup - gapE;
-			const int Ev = t1 > t2 ? t1 : t2;
-			const int de3 = t1 > t2 ? 1 : 0;
-			const int e1 = Ev > 0 ? Ev : 0;
-			const int T2 = Hdg + s;
-			const int Y = e1 > T2 ? e1 : T2;
-			/* in-row gap: inclusive max-plus scan of A = Y - gapO with decay g per column */
-			int P = act ? Y - gapO : SSW_TB_NEGINF;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const int o = __shfl_up_sync(FULL, P, d);
-				if (lane >= d) P = max(P, o - d * g);
-			}
-			const int Pm1 = __shfl_up_sync(FULL, P, 1);
-			const int Fv = lane == 0 ? carryF : max(Pm1, carryF - lane * g);
-			const int Hv = Y > Fv ? Y : Fv;
-			/* df from the left neighbour's H and F */
-			int Hl = __shfl_up_sync(FULL, Hv, 1), Fl = __shfl_up_sync(FULL, Fv, 1);
-			if (lane == 0) { Hl = carryH; Fl = carryFp; }
-			int df5;
-			if (j == beg) df5 = 1;                               /* 0 - gapO > neg_inf - gapE */
-			else df5 = (Hl - gapO > Fl - gapE) ? 1 : 0;
-			const int f1 = Fv > 0 ? Fv : 0;
-			const int T1 = e1 > f1 ? e1 : f1;
-			const int hsel = T1 <= T2 ? 0 : (e1 > f1 ? 1 : 2);
+			int Hv, Ev, dirb;
+			ssw_tb_tile(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryH, carryFp, Hv, Ev, dirb);
 			if (act) {
 				Hrow[cur][j] = Hv;
 				Erow[cur][j] = Ev;
-				drow[j] = (uint8_t)(de3 | (df5 << 1) | (hsel << 2));
+				drow[j] = (uint8_t)dirb;
 				if (Hv > bestv) { bestv = Hv; besti = i; bestj = j; }
 			}
-			/* carries into the next tile */
-			const int P31 = __shfl_sync(FULL, P, 31);
-			carryH = __shfl_sync(FULL, Hv, 31);
-			carryFp = __shfl_sync(FULL, Fv, 31);
-			carryF = max(P31, carryF - 32 * g);
 		}
 		__syncwarp();
 	}
@@ -322,15 +378,18 @@ ssw_banded_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
 }
 
 /*
- * Host driver of P3: band-doubling rounds (ssw.c:616-680) and the full-band
- * retry of ssw_align (:945-957).  `emit(i, words, len, failed)` is called once
- * per task with the final CIGAR (failed != 0: banded_sw gave up -> flag 1).
+ * Host driver of P3: band-doubling rounds (ssw.c:616-680) and the full-band retry of ssw_align (:945-957).
+ * A round groups the unfinished tasks by kernel shape (row-ring width; 0 = global-memory kernel) and launches the
+ * groups concurrently on separate streams: every task is a latency-bound chain (row after row), so a launch lasts
+ * as long as its slowest task and overlapping the groups hides most of that.  `emit(i, words, len, failed)` is
+ * called once per task with the final CIGAR (failed != 0: banded_sw gave up -> flag 1).
  */
 static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
                              const int8_t* d_q, const int8_t* d_r, const int8_t* d_mat, int n, int gapO, int gapE,
                              SswDevBuf* scratch, float* ms_acc, int64_t* launches,
                              const std::function<int(size_t, const uint32_t*, int32_t, int)>& emit)
 {
+	static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
 	std::vector<size_t> active(tasks.size());
 	for (size_t i = 0; i < tasks.size(); ++i) {
 		SswTbTask& t = tasks[i];
@@ -342,24 +401,27 @@ static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);
 	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + scratch->cap) / 2);
-	SswTimer tm;
-	std::vector<uint32_t> cig_host;
 	auto ring_of = [](const SswTbTask& t) -> int {          /* 0: single-warp kernel with global row buffers */
 		if (t.bw > g_ssw_tb_maxbw) return 0;
 		int r = 256;
+		while (r < 2 * (4 * t.bw) + 66 && r < 2048) r <<= 1;    /* room for two in-kernel doublings */
 		while (r < 2 * t.bw + 66) r <<= 1;
 		return r;
 	};
+	SswTimer tm;
+	std::vector<uint32_t> cig_host;
 	while (!active.empty()) {
-		/* one launch = tasks of one kernel shape (ring width), as many as fit the scratch budget */
+		/* the round: tasks in kernel-shape order, as many as fit the scratch budget */
 		std::stable_sort(active.begin(), active.end(), [&](size_t x, size_t y) { return ring_of(tasks[x]) < ring_of(tasks[y]); });
-		const int ring = ring_of(tasks[active[0]]);
 		std::vector<size_t> batch;
-		size_t dir_bytes = 0, row_ints = 0, cig_words = 0;
-		size_t k = 0;
-		for (; k < active.size() && ring_of(tasks[active[k]]) == ring; ++k) {
+		std::vector<int> batch_ring;
+		size_t dir_bytes = 0, row_ints = 0, cig_words = 0, k = 0;
+		for (; k < active.size(); ++k) {
 			SswTbTask& t = tasks[active[k]];
-			const size_t d = ((size_t)(2 * (size_t)t.bw + 1) * (size_t)t.read_len + 2 + 15) / 16 * 16;
+			const int ring = ring_of(t);
+			size_t bw_last = (size_t)t.bw;                          /* widest band the kernel may reach by itself */
+			if (ring) while (2 * (2 * bw_last) + 66 <= (size_t)ring && 2 * bw_last <= (size_t)std::max(t.ref_len, t.read_len)) bw_last *= 2;
+			const size_t d = ((2 * bw_last + 1) * (size_t)t.read_len + 2 + 15) / 16 * 16;
 			const size_t r = ring ? 0 : 4 * ((size_t)t.ref_len + 2);
 			const size_t c = (size_t)t.ref_len + (size_t)t.read_len + 4;
 			const size_t need = dir_bytes + d + 4 * (row_ints + r) + 4 * (cig_words + c) + sizeof(SswTbTask) * (batch.size() + 1) + 1024;
@@ -367,6 +429,7 @@ static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
 			t.dir_off = (int64_t)dir_bytes; t.row_off = (int64_t)row_ints; t.cig_off = (int64_t)cig_words;
 			dir_bytes += d; row_ints += r; cig_words += c;
 			batch.push_back(active[k]);
+			batch_ring.push_back(ring);
 		}
 		std::vector<size_t> rest(active.begin() + k, active.end());
 		const size_t off_rows = (dir_bytes + 255) / 256 * 256;
@@ -378,25 +441,48 @@ static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
 		for (size_t i = 0; i < batch.size(); ++i) bt[i] = tasks[batch[i]];
 		uint8_t* base = scratch->as<uint8_t>();
 		SswTbTask* d_tasks = reinterpret_cast<SswTbTask*>(base + off_tasks);
+		uint32_t* d_cig = reinterpret_cast<uint32_t*>(base + off_cig);
 		SSW_CUDA_OK(cudaMemcpyAsync(d_tasks, bt.data(), sizeof(SswTbTask) * bt.size(), cudaMemcpyHostToDevice, stream));
+		SSW_CUDA_OK(cudaStreamSynchronize(stream));
 		tm.start(stream);
-		if (ring) {
-			const size_t smem = (size_t)SSW_TBP_SLOTS * 2 * (size_t)ring * sizeof(int32_t);
-			if (smem > 48 * 1024) SSW_CUDA_OK(cudaFuncSetAttribute(ssw_banded_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			ssw_launch(ssw_banded_rows_kernel, dim3((unsigned)bt.size()), dim3(SSW_TBP_WARPS * 32), smem, stream,
-			           d_tasks, d_q, d_r, d_mat, n, gapO, gapE, base, reinterpret_cast<uint32_t*>(base + off_cig), ring);
-		} else {
-			ssw_launch(ssw_banded_kernel, dim3(((int)bt.size() + SSW_TB_WARPS - 1) / SSW_TB_WARPS), dim3(SSW_TB_THREADS), 0, stream,
-			           d_tasks, (int)bt.size(), d_q, d_r, d_mat, n, gapO, gapE,
-			           base, reinterpret_cast<int32_t*>(base + off_rows), reinterpret_cast<uint32_t*>(base + off_cig));
+		/* one launch per kernel shape, each on its own stream */
+		int n_groups = 0;
+		for (size_t g0 = 0; g0 < bt.size();) {
+			size_t g1 = g0;
+			while (g1 < bt.size() && batch_ring[g1] == batch_ring[g0]) ++g1;
+			const int ring = batch_ring[g0], cnt = (int)(g1 - g0);
+			cudaStream_t st = stream;
+			if (n_groups > 0) {
+				const int si = (n_groups - 1) % 3;
+				if (!side[si]) SSW_CUDA_OK(cudaStreamCreateWithFlags(&side[si], cudaStreamNonBlocking));
+				st = side[si];
+			}
+			const dim3 grid((cnt + SSW_TB_WARPS - 1) / SSW_TB_WARPS);
+			if (ring) {
+				const size_t smem = (size_t)SSW_TB_WARPS * 4 * (size_t)ring * sizeof(int32_t) + (size_t)n * n + 16;
+				if (smem > 48 * 1024) SSW_CUDA_OK(cudaFuncSetAttribute(ssw_banded_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				ssw_launch(ssw_banded_smem_kernel, grid, dim3(SSW_TB_THREADS), smem, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE, base, d_cig, ring);
+			} else {
+				ssw_launch(ssw_banded_kernel, grid, dim3(SSW_TB_THREADS), 0, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE,
+				           base, reinterpret_cast<int32_t*>(base + off_rows), d_cig);
+			}
+			SSW_CUDA_OK(cudaGetLastError());
+			*launches += 1;
+			++n_groups;
+			g0 = g1;
 		}
-		SSW_CUDA_OK(cudaGetLastError());
+		for (int si = 0; si < 3 && si < n_groups - 1; ++si) SSW_CUDA_OK(cudaStreamSynchronize(side[si]));
 		*ms_acc += tm.stop(stream);
-		*launches += 1;
 		SSW_CUDA_OK(cudaMemcpyAsync(bt.data(), d_tasks, sizeof(SswTbTask) * bt.size(), cudaMemcpyDeviceToHost, stream));
 		cig_host.resize(cig_words);
 		SSW_CUDA_OK(cudaMemcpyAsync(cig_host.data(), base + off_cig, cig_words * 4, cudaMemcpyDeviceToHost, stream));
 		SSW_CUDA_OK(cudaStreamSynchronize(stream));
+		if (getenv("SSW_TRACE")) {
+			double f = 0, w = 0, s = 0; int nf = 0; long long fmax = 0, wmax = 0;
+			for (const SswTbTask& x : bt) { f += (double)x.dbg_fill; fmax = std::max<long long>(fmax, x.dbg_fill); if (x.dbg_walk) { w += (double)x.dbg_walk; s += (double)x.dbg_score; wmax = std::max<long long>(wmax, x.dbg_walk); ++nf; } }
+			fprintf(stderr, "[libssw-b200 trace] traceback round: %zu tasks in %d launches | fill avg %.0f max %lld clk | %d finished: walk avg %.0f max %lld, rescore avg %.0f clk\n",
+			        bt.size(), n_groups, f / bt.size(), fmax, nf, nf ? w / nf : 0.0, wmax, nf ? s / nf : 0.0);
+		}
 		std::vector<size_t> next;
 		for (size_t i = 0; i < batch.size(); ++i) {
 			SswTbTask& t = tasks[batch[i]];

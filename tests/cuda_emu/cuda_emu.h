@@ -152,6 +152,7 @@ template <class T> static inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; r
 
 /* ---- scalar + SIMD-in-word intrinsics ------------------------------------- */
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline long long clock64() { return 0; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
