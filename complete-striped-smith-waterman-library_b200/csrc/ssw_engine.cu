@@ -16,6 +16,7 @@
 #include <vector>
 #include <string>
 #include <string.h>
+#include <math.h>
 #include <functional>
 
 #include "ssw_common.cuh"
@@ -169,6 +170,43 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, i
 	*ms_acc += t_k.stop(stream);
 	tr.lap("  fill: wait");
 	return rc;
+}
+
+
+/* resident CTAs per SM of the forward fill kernel of instance `inst` in CTA-shared-profile mode */
+template <int G, int R>
+static int fill_occ_of(int n)
+{
+	int occ = 0;
+	const size_t smem = ssw_fill_smem_bytes<R>(n, 1);
+	auto kern = ssw_fill_kernel<G, R, 1, true, false>;
+	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSW_FILL_THREADS, smem) != cudaSuccess) occ = 1;
+	return occ;
+}
+static int fill_occupancy(int inst, int n)
+{
+	static int cache[16][65];
+	if (inst < 0 || inst >= 16 || n < 0 || n > 64) return 1;
+	if (cache[inst][n]) return cache[inst][n];
+	int occ = 1;
+	switch (inst) {
+	case 0: occ = fill_occ_of<8, 4>(n); break;
+	case 1: occ = fill_occ_of<8, 5>(n); break;
+	case 2: occ = fill_occ_of<8, 8>(n); break;
+	case 3: occ = fill_occ_of<8, 10>(n); break;
+	case 4: occ = fill_occ_of<8, 16>(n); break;
+	case 5: occ = fill_occ_of<8, 20>(n); break;
+	case 6: occ = fill_occ_of<16, 16>(n); break;
+	case 7: occ = fill_occ_of<16, 20>(n); break;
+	case 8: occ = fill_occ_of<32, 16>(n); break;
+	case 9: occ = fill_occ_of<32, 20>(n); break;
+	case 14: occ = fill_occ_of<16, 10>(n); break;
+	case 15: occ = fill_occ_of<32, 10>(n); break;
+	default: break;
+	}
+	cache[inst][n] = occ > 0 ? occ : 1;
+	return cache[inst][n];
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -593,40 +631,65 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			++k_end;
 		}
 		const int64_t target_items = (int64_t)e->sm_count * 32 * 8;
-		const int64_t auto_chunk = (total_cols / target_items + 3) / 4 * 4;
+		const int64_t base_chunk = (total_cols / target_items + 3) / 4 * 4;
 
 		/* chunk every pair-task; a multi-chunk pair-task gets a multiple of per_cta chunks so that its CTAs are full */
 		struct Plan { int32_t n_chunks, chunk, warm; };
 		std::vector<Plan> plan(k_end - k);
-		int64_t live_items = 0, padded_items = 0, run_items = 0;
-		for (size_t i = k; i < k_end; ++i) {
-			const PT& pt = pts[i];
-			const Aln& A = alns[pt.a];
-			const Aln* B = pt.b >= 0 ? &alns[pt.b] : nullptr;
-			const int32_t ref_len = e->r_len[pt.r];
-			const int max_lp = std::max(lp_of(A.read_len, word), B ? lp_of(B->read_len, word) : 0);
-			const int max_len = std::max(A.read_len, B ? B->read_len : 0);
-			/* a path with positive score spans at most max_lp diagonal steps plus (total positive score)/gapE gap columns */
-			int64_t warm = 0, chunk = ref_len;
-			if (P.gap_extend > 0 && S.max_mat > 0) {
-				warm = (int64_t)max_lp + ((int64_t)max_len * S.max_mat + P.gap_extend - 1) / P.gap_extend + 4;
-				warm = (warm + 3) / 4 * 4;
-				chunk = e->opt_chunk > 0 ? e->opt_chunk : std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
+		int64_t live_items = 0, padded_items = 0;
+		auto make_plan = [&](int64_t auto_chunk, double* warm_frac) {
+			int64_t run_items = 0, cols = 0, warm_cols = 0;
+			live_items = 0; padded_items = 0;
+			for (size_t i = k; i < k_end; ++i) {
+				const PT& pt = pts[i];
+				const Aln& A = alns[pt.a];
+				const Aln* B = pt.b >= 0 ? &alns[pt.b] : nullptr;
+				const int32_t ref_len = e->r_len[pt.r];
+				const int max_lp = std::max(lp_of(A.read_len, word), B ? lp_of(B->read_len, word) : 0);
+				const int max_len = std::max(A.read_len, B ? B->read_len : 0);
+				/* a path with positive score spans at most max_lp diagonal steps plus (total positive score)/gapE gap columns */
+				int64_t warm = 0, chunk = ref_len;
+				if (P.gap_extend > 0 && S.max_mat > 0) {
+					warm = (int64_t)max_lp + ((int64_t)max_len * S.max_mat + P.gap_extend - 1) / P.gap_extend + 4;
+					warm = (warm + 3) / 4 * 4;
+					chunk = e->opt_chunk > 0 ? e->opt_chunk : std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
+				}
+				int64_t n_chunks = chunk >= ref_len ? 1 : (ref_len + chunk - 1) / chunk;
+				if (n_chunks > 1 && e->opt_chunk == 0) {
+					n_chunks = (n_chunks + per_cta - 1) / per_cta * per_cta;
+					chunk = ((ref_len + n_chunks - 1) / n_chunks + 3) / 4 * 4;
+					n_chunks = (ref_len + chunk - 1) / chunk;
+				}
+				if (n_chunks == 1) chunk = std::max<int32_t>((ref_len + 3) / 4 * 4, 4);
+				plan[i - k] = Plan{(int32_t)n_chunks, (int32_t)chunk, (int32_t)warm};
+				live_items += n_chunks;
+				cols += ref_len; warm_cols += (n_chunks - 1) * warm;
+				const bool new_run = i == k || pts[i].qa != pts[i - 1].qa || pts[i].qb != pts[i - 1].qb;
+				if (new_run) { padded_items += (run_items + per_cta - 1) / per_cta * per_cta; run_items = 0; }
+				run_items += n_chunks;
 			}
-			int64_t n_chunks = chunk >= ref_len ? 1 : (ref_len + chunk - 1) / chunk;
-			if (n_chunks > 1 && e->opt_chunk == 0) {
-				n_chunks = (n_chunks + per_cta - 1) / per_cta * per_cta;
-				chunk = ((ref_len + n_chunks - 1) / n_chunks + 3) / 4 * 4;
-				n_chunks = (ref_len + chunk - 1) / chunk;
+			padded_items += (run_items + per_cta - 1) / per_cta * per_cta;
+			if (warm_frac) *warm_frac = cols > 0 ? (double)warm_cols / (double)cols : 0.0;
+		};
+		/* Wave quantisation: the CTAs of such a launch all take about the same time, so the launch lasts
+		 * ceil(CTAs / resident CTAs) CTA-times.  Try chunk lengths around the default and keep the one with the best
+		 * (fill of the last wave) x (1 - warm-up overhead). */
+		int64_t auto_chunk = base_chunk;
+		if (e->opt_chunk == 0 && base_chunk >= 4096) {
+			const int occ = fill_occupancy(inst, P.n);
+			const double slots = (double)e->sm_count * std::max(occ, 1);
+			double best_eff = -1;
+			for (int pct = 60; pct <= 150; pct += 5) {
+				const int64_t c = (base_chunk * pct / 100 + 3) / 4 * 4;
+				double wf = 0;
+				make_plan(c, &wf);
+				const double ctas = (double)((live_items + per_cta - 1) / per_cta);
+				const double waves = ctas / slots;
+				const double eff = (waves / ceil(waves - 1e-9)) / (1.0 + wf);
+				if (eff > best_eff + 1e-6) { best_eff = eff; auto_chunk = c; }
 			}
-			if (n_chunks == 1) chunk = std::max<int32_t>((ref_len + 3) / 4 * 4, 4);
-			plan[i - k] = Plan{(int32_t)n_chunks, (int32_t)chunk, (int32_t)warm};
-			live_items += n_chunks;
-			const bool new_run = i == k || pts[i].qa != pts[i - 1].qa || pts[i].qb != pts[i - 1].qb;
-			if (new_run) { padded_items += (run_items + per_cta - 1) / per_cta * per_cta; run_items = 0; }
-			run_items += n_chunks;
 		}
-		padded_items += (run_items + per_cta - 1) / per_cta * per_cta;
+		make_plan(auto_chunk, nullptr);
 		const int share = padded_items * 100 <= live_items * 112 ? 1 : 0;
 
 		std::vector<SswItem> items;

@@ -267,7 +267,7 @@ __device__ static __forceinline__ void ssw_reduce_best(const SswLaneBest& lb, in
 /* ---------------------------------------------------------------------------------------------------------- */
 
 #ifndef SSW_FILL_MINB
-#define SSW_FILL_MINB 1                     /* minimum resident CTAs per SM asked of ptxas (register cap) */
+#define SSW_FILL_MINB 4                     /* minimum resident CTAs per SM asked of ptxas: 128 registers; 16 warps/SM measured 3 % faster than 12 */
 #endif
 template <int G, int R, int DIR, bool WRITE_CM, bool TERM>
 __global__ void __launch_bounds__(SSW_FILL_THREADS, SSW_FILL_MINB)
