@@ -25,6 +25,7 @@
 #include "ssw_resolve.cuh"
 #include "ssw_traceback.cuh"
 #include "ssw_emul.cuh"
+#include "ssw_grid.cuh"
 #include "../../include/ssw_batch.h"
 
 #include <chrono>
@@ -53,6 +54,7 @@ static const int kNumFwd = 10;
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 
 static int g_strip_super = SSW_STRIP_SUPER;   /* columns per super-block of the strip kernel ("super" option, tests) */
+static int g_grid_min_pairs = 32768;    /* "grid_min" option: smaller grids use the general path */
 static int g_force_inst = -1;      /* experiment knob ("inst" option): use this instance whenever it covers the query */
 static int pick_inst(int lp)
 {
@@ -87,7 +89,7 @@ struct ssw_engine {
 	SswDevBuf d_q, d_r, d_mat;
 
 	/* scratch */
-	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul;
+	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out;
 	int64_t opt_chunk = 0;
 	ssw_engine_timing timing;
 	SswTimer t_total, t_k;
@@ -240,7 +242,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 {
 	if (!e) return;
 	cudaSetDevice(e->device);
-	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul};
+	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out};
 	for (SswDevBuf* b : bufs) b->release();
 	if (e->stream) cudaStreamDestroy(e->stream);
 	delete e;
@@ -252,6 +254,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 {
 	if (!e || !name) return -1;
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
+	if (!strcmp(name, "grid_min")) { g_grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
 	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }       /* index into kInst */
 	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 3) / 4 * 4 : SSW_STRIP_SUPER; return 0; }
 	if (!strcmp(name, "tb_maxbw")) { g_ssw_tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
@@ -877,39 +880,160 @@ static int emul_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>&
 	return 0;
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* large grids, scores only: descriptors planned on the device (ssw_grid.cuh)                     */
+/* ------------------------------------------------------------------------------------------- */
+
+
+/* Returns 1 when the grid path handled the batch (results filled; `redo` lists pairs to re-do by the general path),
+ * 0 when the batch is not eligible, < 0 on error. */
+static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, int64_t n_pairs,
+                       ssw_batch_result* results, std::vector<int32_t>* redo)
+{
+	if (n_pairs != (int64_t)e->n_q * e->n_r || n_pairs < g_grid_min_pairs || n_pairs > 0x7fffffff) return 0;
+	if (P.flag != 0 || P.gap_open <= P.gap_extend || e->opt_chunk != 0) return 0;
+	if (!S.has_byte && !S.has_word) return 0;
+	const int word = S.has_byte ? 0 : 1;
+	const int limit = word ? S.limit_word : S.limit_byte;
+	const int n_q = e->n_q, n_r = e->n_r;
+	for (int r = 0; r < n_r; ++r) if (e->r_len[r] > 4096) return 0;          /* one chunk per reference only */
+	std::vector<SswGridQ> qt((size_t)n_q);
+	std::vector<int> q_inst((size_t)n_q);
+	for (int q = 0; q < n_q; ++q) {
+		const int len = (int)(e->q_off[q + 1] - e->q_off[q]);
+		if (len < 1) return 0;
+		if (S.has_byte && S.has_word && (int64_t)len * std::max(S.max_mat, 0) >= 2 * (int64_t)S.limit_byte) return 0;   /* word-first prediction: general path */
+		qt[q].off = (int32_t)e->q_off[q]; qt[q].len = len; qt[q].lp = lp_of(len, word);
+		qt[q].mask_len = P.mask_len < 0 ? len / 2 : P.mask_len;
+		q_inst[q] = pick_inst(qt[q].lp);
+		if (q_inst[q] < 0) return 0;
+	}
+	Trace tr;
+	std::vector<int32_t> order((size_t)n_q);
+	for (int q = 0; q < n_q; ++q) order[q] = q;
+	std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+		if (q_inst[x] != q_inst[y]) return q_inst[x] < q_inst[y];
+		if (qt[x].lp != qt[y].lp) return qt[x].lp < qt[y].lp;
+		return x < y;
+	});
+	/* reference tables */
+	std::vector<int64_t> cm_prefix((size_t)n_r);
+	int64_t cm_per_qp = 0;
+	for (int r = 0; r < n_r; ++r) { cm_prefix[r] = cm_per_qp; cm_per_qp += ((int64_t)e->r_len[r] + 3) / 4 * 4; }
+	/* static tables on the device: [qt][ref_off][ref_len][cm_prefix] */
+	const size_t o_qt = 0, o_roff = o_qt + (sizeof(SswGridQ) * n_q + 255) / 256 * 256, o_rlen = o_roff + (8 * (size_t)n_r + 255) / 256 * 256;
+	const size_t o_cmp = o_rlen + (4 * (size_t)n_r + 255) / 256 * 256, o_qp = o_cmp + (8 * (size_t)n_r + 255) / 256 * 256;
+	const size_t o_cnt = o_qp + (8 * (size_t)(n_q / 2 + 1) + 255) / 256 * 256, o_list = o_cnt + 256;
+	const int32_t redo_cap = (int32_t)std::min<int64_t>(n_pairs, 1 << 22);
+	if (e->d_grid.ensure(o_list + 4 * (size_t)redo_cap)) return -1;
+	uint8_t* gb = e->d_grid.as<uint8_t>();
+	SSW_CUDA_OK(cudaMemcpyAsync(gb + o_qt, qt.data(), sizeof(SswGridQ) * n_q, cudaMemcpyHostToDevice, e->stream));
+	SSW_CUDA_OK(cudaMemcpyAsync(gb + o_roff, e->r_off.data(), 8 * (size_t)n_r, cudaMemcpyHostToDevice, e->stream));
+	SSW_CUDA_OK(cudaMemcpyAsync(gb + o_rlen, e->r_len.data(), 4 * (size_t)n_r, cudaMemcpyHostToDevice, e->stream));
+	SSW_CUDA_OK(cudaMemcpyAsync(gb + o_cmp, cm_prefix.data(), 8 * (size_t)n_r, cudaMemcpyHostToDevice, e->stream));
+	SSW_CUDA_OK(cudaMemsetAsync(gb + o_cnt, 0, 256, e->stream));
+	if (e->d_out.ensure(sizeof(ssw_batch_result) * (size_t)n_pairs)) return -1;
+
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	const size_t budget = std::max<size_t>((size_t)256 << 20, (free_b + e->d_colmax.cap + e->d_items.cap + e->d_alns.cap + e->d_res.cap) / 2);
+	tr.lap("grid: tables");
+	size_t k = 0;
+	while (k < order.size()) {
+		const int inst = q_inst[order[k]];
+		const int per_cta = SSW_FILL_WARPS * (32 / kInst[inst].G);
+		const int n_r_pad = (n_r + per_cta - 1) / per_cta * per_cta;
+		/* query pairs of this launch: same instance, bounded by memory */
+		const size_t per_qp = (size_t)cm_per_qp * 4 + (size_t)n_r_pad * (sizeof(SswItem) + sizeof(SswItemBest)) + (size_t)n_r * 2 * (sizeof(SswAlnDesc) + sizeof(SswFillResult));
+		const size_t max_qp = std::max<size_t>(1, budget / per_qp);
+		std::vector<int2> qps;
+		while (k < order.size() && q_inst[order[k]] == inst && qps.size() < max_qp) {
+			int2 pr = make_int2(order[k], -1);
+			++k;
+			if (k < order.size() && q_inst[order[k]] == inst) { pr.y = order[k]; ++k; }
+			qps.push_back(pr);
+		}
+		SswGridArgs A;
+		A.n_qp = (int32_t)qps.size(); A.n_r = n_r; A.n_r_pad = n_r_pad; A.word = word; A.limit = limit; A.pad_ = 0; A.cm_words_per_qp = cm_per_qp;
+		const int64_t n_items = (int64_t)A.n_qp * n_r_pad, n_desc = (int64_t)A.n_qp * n_r * 2;
+		if (n_items > 0x7fffffff || n_desc > 0x7fffffff) return 0;
+		if (e->d_items.ensure(sizeof(SswItem) * (size_t)n_items)) return -1;
+		if (e->d_bests.ensure(sizeof(SswItemBest) * (size_t)n_items)) return -1;
+		if (e->d_alns.ensure(sizeof(SswAlnDesc) * (size_t)n_desc)) return -1;
+		if (e->d_res.ensure(sizeof(SswFillResult) * (size_t)n_desc)) return -1;
+		if (e->d_colmax.ensure((size_t)A.n_qp * (size_t)cm_per_qp * 4 + 64)) return -1;
+		SSW_CUDA_OK(cudaMemcpyAsync(gb + o_qp, qps.data(), sizeof(int2) * qps.size(), cudaMemcpyHostToDevice, e->stream));
+		e->t_k.start(e->stream);
+		ssw_launch(ssw_grid_plan_kernel, dim3((unsigned)((n_items + 255) / 256)), dim3(256), 0, e->stream, A,
+		           (const int2*)reinterpret_cast<int2*>(gb + o_qp), (const SswGridQ*)reinterpret_cast<SswGridQ*>(gb + o_qt),
+		           (const int64_t*)reinterpret_cast<int64_t*>(gb + o_roff), (const int32_t*)reinterpret_cast<int32_t*>(gb + o_rlen),
+		           (const int64_t*)reinterpret_cast<int64_t*>(gb + o_cmp), e->d_items.as<SswItem>(), e->d_alns.as<SswAlnDesc>());
+		SSW_CUDA_OK(cudaGetLastError());
+		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		e->timing.other_launches += 1;
+		/* fill (items are already on the device) */
+		{
+			e->t_k.start(e->stream);
+			int rc = -1;
+			switch (inst) {
+			case 0: rc = launch_fill<8, 4>(e, (int)n_items, +1, 1, P); break;
+			case 1: rc = launch_fill<8, 5>(e, (int)n_items, +1, 1, P); break;
+			case 2: rc = launch_fill<8, 8>(e, (int)n_items, +1, 1, P); break;
+			case 3: rc = launch_fill<8, 10>(e, (int)n_items, +1, 1, P); break;
+			case 4: rc = launch_fill<8, 16>(e, (int)n_items, +1, 1, P); break;
+			case 5: rc = launch_fill<8, 20>(e, (int)n_items, +1, 1, P); break;
+			case 6: rc = launch_fill<16, 16>(e, (int)n_items, +1, 1, P); break;
+			case 7: rc = launch_fill<16, 20>(e, (int)n_items, +1, 1, P); break;
+			case 8: rc = launch_fill<32, 16>(e, (int)n_items, +1, 1, P); break;
+			case 9: rc = launch_fill<32, 20>(e, (int)n_items, +1, 1, P); break;
+			default: break;
+			}
+			if (rc) return rc < 0 ? rc : -1;
+			e->timing.fill_forward_ms += e->t_k.stop(e->stream);
+			e->timing.fill_forward_launches += 1;
+			e->timing.cells_forward += (int64_t)A.n_qp * (cm_per_qp) * kInst[inst].G * kInst[inst].R * 2;
+		}
+		e->t_k.start(e->stream);
+		{
+			const int per = SSW_RESOLVE_THREADS / 32;
+			ssw_launch(ssw_resolve_kernel<true>, dim3((unsigned)((n_desc + per - 1) / per)), dim3(SSW_RESOLVE_THREADS), 0, e->stream,
+			           (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(), (int)n_desc, (const SswItemBest*)e->d_bests.as<SswItemBest>(),
+			           (const uint32_t*)e->d_colmax.as<uint32_t>(), e->d_res.as<SswFillResult>());
+			ssw_launch(ssw_grid_emit_kernel, dim3((unsigned)((n_desc + 255) / 256)), dim3(256), 0, e->stream, A,
+			           (const int2*)reinterpret_cast<int2*>(gb + o_qp), (const SswGridQ*)reinterpret_cast<SswGridQ*>(gb + o_qt),
+			           (const SswFillResult*)e->d_res.as<SswFillResult>(), e->d_out.as<ssw_batch_result>(),
+			           reinterpret_cast<int32_t*>(gb + o_list), reinterpret_cast<int32_t*>(gb + o_cnt), redo_cap);
+			SSW_CUDA_OK(cudaGetLastError());
+		}
+		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		e->timing.other_launches += 2;
+		tr.lap("grid: launch group");
+	}
+	int32_t n_redo = 0;
+	SSW_CUDA_OK(cudaMemcpyAsync(&n_redo, gb + o_cnt, 4, cudaMemcpyDeviceToHost, e->stream));
+	SSW_CUDA_OK(cudaMemcpyAsync(results, e->d_out.p, sizeof(ssw_batch_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, e->stream));
+	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	if (n_redo > redo_cap) {                     /* more overflows than the list holds: find them by scanning is not possible -> general path */
+		return 0;
+	}
+	redo->resize((size_t)n_redo);
+	if (n_redo) {
+		SSW_CUDA_OK(cudaMemcpy(redo->data(), gb + o_list, 4 * (size_t)n_redo, cudaMemcpyDeviceToHost));
+		std::sort(redo->begin(), redo->end());
+	}
+	tr.lap("grid: results d2h");
+	return 1;
+}
+
 }  // namespace
 
-extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
-                                int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
-                                ssw_batch_result* results,
-                                uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
+/* The general path: any pair list, any flag. */
+static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
+                         int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                         ssw_batch_result* results, uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
 {
-	if (!e || !params || !params->mat || n_pairs < 0 || (n_pairs && !results)) return -1;
-	const ssw_batch_params& P = *params;
-	if (P.n < 1 || P.n > 64) { fprintf(stderr, "[libssw-b200] alphabet size %d not supported (1..64)\n", P.n); return -1; }
-	if ((pair_query == nullptr) != (pair_ref == nullptr)) return -1;
-	int64_t pool_used_local = 0;
-	if (!pool_used) pool_used = &pool_used_local;
-	*pool_used = 0;
-	SSW_CUDA_OK(cudaSetDevice(e->device));
-	memset(&e->timing, 0, sizeof(e->timing));
-	if (n_pairs == 0) return 0;
 	/* gapO <= gapE: the reference's result depends on its SIMD layout (lazy-F exit); use the lane-literal kernel */
 	const bool literal = P.gap_open <= P.gap_extend;
-	e->t_total.start(e->stream);
-
-	/* scoring matrix: bias = |min(mat)| for byte semantics (ssw.c:834-838) */
-	Sem S;
-	S.bias = 0; S.max_mat = -128;
-	for (int i = 0; i < P.n * P.n; ++i) { if (P.mat[i] < S.bias) S.bias = P.mat[i]; if (P.mat[i] > S.max_mat) S.max_mat = P.mat[i]; }
-	S.bias = S.bias < 0 ? -S.bias : S.bias;
-	S.limit_byte = 255 - S.bias;
-	S.limit_word = 32767 - std::max(S.max_mat, 0) - 256;
-	S.has_byte = P.score_size == 0 || P.score_size == 2;
-	S.has_word = P.score_size == 1 || P.score_size == 2;
-	if (e->d_mat.ensure((size_t)P.n * P.n + 16)) return -1;
-	SSW_CUDA_OK(cudaMemcpyAsync(e->d_mat.p, P.mat, (size_t)P.n * P.n, cudaMemcpyHostToDevice, e->stream));
-	if (e->upload_refs(P.n)) return -1;
 
 	std::vector<Aln> alns((size_t)n_pairs);
 	for (int64_t p = 0; p < n_pairs; ++p) {
@@ -1044,6 +1168,59 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 			*pool_used += len;
 			return 0;
 		});
+		if (rc) return rc;
+	}
+	return 0;
+}
+
+extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
+                                int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                                ssw_batch_result* results,
+                                uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
+{
+	if (!e || !params || !params->mat || n_pairs < 0 || (n_pairs && !results)) return -1;
+	const ssw_batch_params& P = *params;
+	if (P.n < 1 || P.n > 64) { fprintf(stderr, "[libssw-b200] alphabet size %d not supported (1..64)\n", P.n); return -1; }
+	if ((pair_query == nullptr) != (pair_ref == nullptr)) return -1;
+	int64_t pool_used_local = 0;
+	if (!pool_used) pool_used = &pool_used_local;
+	*pool_used = 0;
+	SSW_CUDA_OK(cudaSetDevice(e->device));
+	memset(&e->timing, 0, sizeof(e->timing));
+	if (n_pairs == 0) return 0;
+	e->t_total.start(e->stream);
+
+	/* scoring matrix: bias = |min(mat)| for byte semantics (ssw.c:834-838) */
+	Sem S;
+	S.bias = 0; S.max_mat = -128;
+	for (int i = 0; i < P.n * P.n; ++i) { if (P.mat[i] < S.bias) S.bias = P.mat[i]; if (P.mat[i] > S.max_mat) S.max_mat = P.mat[i]; }
+	S.bias = S.bias < 0 ? -S.bias : S.bias;
+	S.limit_byte = 255 - S.bias;
+	S.limit_word = 32767 - std::max(S.max_mat, 0) - 256;
+	S.has_byte = P.score_size == 0 || P.score_size == 2;
+	S.has_word = P.score_size == 1 || P.score_size == 2;
+	if (e->d_mat.ensure((size_t)P.n * P.n + 16)) return -1;
+	SSW_CUDA_OK(cudaMemcpyAsync(e->d_mat.p, P.mat, (size_t)P.n * P.n, cudaMemcpyHostToDevice, e->stream));
+	if (e->upload_refs(P.n)) return -1;
+
+	int rc = 0;
+	std::vector<int32_t> redo;
+	const int grid = pair_query ? 0 : grid_scores(e, P, S, n_pairs, results, &redo);
+	if (grid < 0) return grid;
+	if (grid == 1) {
+		/* the device-planned grid handled everything except byte overflows: those pairs go through the general path */
+		if (!redo.empty()) {
+			std::vector<int32_t> pq(redo.size()), pr(redo.size());
+			for (size_t i = 0; i < redo.size(); ++i) { pq[i] = redo[i] / e->n_r; pr[i] = redo[i] % e->n_r; }
+			std::vector<ssw_batch_result> sub(redo.size());
+			const ssw_engine_timing keep = e->timing;
+			rc = align_general(e, P, S, (int64_t)redo.size(), pq.data(), pr.data(), sub.data(), cigar_pool, pool_cap, pool_used);
+			if (rc) return rc;
+			for (size_t i = 0; i < redo.size(); ++i) results[redo[i]] = sub[i];
+			e->timing.byte_overflows = keep.byte_overflows + (int64_t)redo.size();
+		}
+	} else {
+		rc = align_general(e, P, S, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_cap, pool_used);
 		if (rc) return rc;
 	}
 	e->timing.total_ms = e->t_total.stop(e->stream);

@@ -154,3 +154,43 @@ def test_emulated_word_saturation(emu, oracle, capfd):
         a = emu.align(q, r, mat, 5, 40, 3, flag, 0, 32767, 50, ss)
         b = oracle.align(q, r, mat, 5, 40, 3, flag, 0, 32767, 50, ss)
         assert b["score1"] >= 32000 and C.diff_results(a, b) == [], (qlen, flag, ss)
+
+
+def test_emulated_device_planned_grid(oracle, capfd):
+    """Full grids with flag 0 are planned on the device (ssw_grid.cuh); byte overflows come back through the general
+    path.  Forced here for a small grid with the "grid_min" option."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("grid_min", 1)
+    rng = np.random.default_rng(31)
+    mat = C.dna_matrix(2, 2)
+    refs = [rng.integers(0, 4, size=n).astype(np.int8) for n in (260, 97, 400, 33, 180)]
+    queries = []
+    for i, n in enumerate((150, 150, 140, 33, 64, 17, 150, 100, 1)):
+        r = refs[(2 * i) % len(refs)]
+        if len(r) > n + 10 and i % 4 != 3:
+            queries.append(C.mutate_read(rng, r, int(rng.integers(0, len(r) - n - 5)), n, 0.02 if i < 3 else 0.1, 0.005, 0.005))
+        else:
+            queries.append(rng.integers(0, 4, size=n).astype(np.int8))
+    eng.set_sequences(queries, refs)
+    for score_size in (2, 1, 0):
+        res, _ = eng.align(mat, 5, 3, 1, flag=0, mask_len=-1, score_size=score_size)
+        k = 0
+        n_over = 0
+        for q in queries:
+            for r in refs:
+                exp = oracle.align(q, r, mat, 5, 3, 1, 0, 0, 0, len(q) // 2, score_size)
+                rr = res[k]
+                if exp is None:
+                    assert int(rr["status"]) == 1, (score_size, k)
+                    n_over += 1
+                else:
+                    got = {f: int(rr[f]) for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
+                    got["cigar"] = []
+                    assert int(rr["status"]) == 0 and C.diff_results(got, exp) == [], (score_size, k)
+                k += 1
+        if score_size == 0:
+            assert n_over > 0          # the high-identity 150-mers overflow 8-bit scores
+    eng.set_option("grid_min", -1)
+    eng.close()
