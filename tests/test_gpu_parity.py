@@ -153,6 +153,47 @@ def test_protein_word_path(engine, checker, capfd):
             k += 1
 
 
+def test_device_planned_grid(engine, checker, capfd):
+    """Config 4 shape through the device-planned grid path (ssw_grid.cuh; forced with grid_min = 1): BLOSUM50 word
+    scores, and a DNA byte-score grid whose overflows are re-done by the general path."""
+    engine.set_option("grid_min", 1)
+    try:
+        rng = np.random.default_rng(4004)
+        queries = [rng.integers(0, 20, size=int(n)).astype(np.int8) for n in (300, 300, 299, 301, 120, 77, 300)]
+        targets = []
+        for t_i in range(60):
+            s = rng.integers(0, 20, size=int(rng.integers(350, 450))).astype(np.int8)
+            if t_i % 5 == 0:
+                q = queries[int(rng.integers(0, 4))]
+                seg = q[40:240].copy()
+                m = rng.random(len(seg)) < 0.2
+                seg[m] = rng.integers(0, 20, size=int(m.sum()))
+                s[60:260] = seg
+            targets.append(s)
+        engine.set_sequences(queries, targets)
+        res, pool = engine.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
+        k = 0
+        for q in queries:
+            for t_ in targets:
+                exp = checker.align(q, t_, C.BLOSUM50, 24, 3, 1, 0, 0, 0, 150, 1)
+                assert C.diff_results(batch_dict(res, pool, k), exp) == [], k
+                k += 1
+        ref, reads = C.make_dna_workload(3000, 40, 150, seed_ref=9, seed_reads=10, p_sub=0.03)
+        refs = [ref[:1500].copy(), ref[1000:].copy(), ref[500:2600].copy()]
+        mat = C.dna_matrix(2, 2)
+        engine.set_sequences(reads, refs)
+        res, pool = engine.align(mat, 5, 3, 1, flag=0, mask_len=-1, score_size=2)
+        assert engine.timing()["byte_overflows"] > 0
+        k = 0
+        for q in reads:
+            for r in refs:
+                exp = checker.align(q, r, mat, 5, 3, 1, 0, 0, 0, 75, 2)
+                assert C.diff_results(batch_dict(res, pool, k), exp) == [], k
+                k += 1
+    finally:
+        engine.set_option("grid_min", -1)
+
+
 def test_byte_overflow_falls_back_to_word(engine, ours, checker, capfd):
     """Scores >= 255 - bias: score_size 2 re-runs with word semantics (ssw.c:883-886); score_size 0 returns NULL (:887-890)."""
     rng = np.random.default_rng(5)
