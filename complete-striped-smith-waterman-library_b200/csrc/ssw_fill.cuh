@@ -41,7 +41,9 @@
 
 #define SSW_FILL_WARPS 4
 #define SSW_FILL_THREADS (SSW_FILL_WARPS * 32)
-#define SSW_STRIP_R 16                      /* rows per lane of the strip kernel: 512 rows per strip */
+#ifndef SSW_STRIP_R
+#define SSW_STRIP_R 10                      /* rows per lane of the strip kernel: 320 rows per strip (config 5: R=10 247 ms, 16: 268, 20: 257, 8: 365) */
+#endif
 #define SSW_STRIP_MAXW 16                   /* warps per CTA of the strip kernel */
 #define SSW_STRIP_LAG 40                    /* a strip's last lane ends a super-block this many columns before the strip above */
 #define SSW_STRIP_SUPER 4096                /* columns per super-block (granularity of early termination) */
