@@ -1,0 +1,42 @@
+/*
+ * TEST INFRASTRUCTURE ONLY.  Stands in for libssw.so's batch entry points with the CPU oracle so that the
+ * host-only logic of ssw_batch_cli (file parsing, option handling, BLAST/SAM formatting, strand choice) can be
+ * checked against the frozen reference outputs on a machine without a GPU.  Never linked into the product.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/ssw.h"
+#include "../../include/ssw_batch.h"
+#include "../../oracle/ssw_oracle.h"
+
+struct ssw_engine { int unused; };
+
+ssw_engine* ssw_engine_create(int device) { (void)device; return (ssw_engine*)calloc(1, sizeof(struct ssw_engine)); }
+void ssw_engine_destroy(ssw_engine* e) { free(e); }
+
+int ssw_align_batch(ssw_engine* e, const ssw_batch_params* P,
+                    int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                    int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
+                    int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out)
+{
+	(void)e; (void)n_queries;
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		const int32_t q = pair_query ? pair_query[p] : (int32_t)(p / n_refs);
+		const int32_t r = pair_ref ? pair_ref[p] : (int32_t)(p % n_refs);
+		const int32_t qlen = (int32_t)(query_off[q + 1] - query_off[q]);
+		oracle_profile* prof = oracle_ssw_init(queries + query_off[q], qlen, P->mat, P->n, P->score_size);
+		const int32_t mask = P->mask_len < 0 ? qlen / 2 : P->mask_len;
+		out[p] = (s_align*)oracle_ssw_align(prof, refs + ref_off[r], (int32_t)(ref_off[r + 1] - ref_off[r]),
+		                                    P->gap_open, P->gap_extend, P->flag, P->filters, P->filterd, mask);
+		oracle_init_destroy(prof);
+	}
+	return 0;
+}
+
+void align_destroy(s_align* a) { oracle_align_destroy((oracle_align_t*)a); }
+
+int32_t mark_mismatch(int32_t ref_begin1, int32_t read_begin1, int32_t read_end1, const int8_t* ref, const int8_t* read,
+                      int32_t readLen, uint32_t** cigar, int32_t* cigarLen)
+{
+	return oracle_mark_mismatch(ref_begin1, read_begin1, read_end1, ref, read, readLen, cigar, cigarLen);
+}

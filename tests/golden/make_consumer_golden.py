@@ -6,6 +6,7 @@ Build container only: reads /root/reference/demo."""
 import json
 import os
 import subprocess
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref")
@@ -13,8 +14,15 @@ DEMO = "/root/reference/demo"
 
 files = {}
 for name in ("r1.fa", "r1_query.fq", "1k.fa", "54mer_hap1_1.100.fa", "protein1.fa", "protein2.fa", "pRef.fa", "pRead.fa",
-             "target.fastq", "query.fastq"):
+             "target.fastq", "query.fastq", "54mer_hap1_1.100.fastq"):
     files[name] = open(os.path.join(DEMO, name)).read()
+# short name: the reference's option parser also scans the characters of an option VALUE as flags (main.c:253-303)
+files["b62.txt"] = open(os.path.join(DEMO, "blosum62.txt")).read()
+
+TMP = tempfile.mkdtemp()
+for name, text in files.items():
+    with open(os.path.join(TMP, name), "w") as f:
+        f.write(text)
 
 runs = []
 for exe, args in [
@@ -27,11 +35,14 @@ for exe, args in [
     ("ssw_test", ["-c", "pRef.fa", "pRead.fa"]),
     ("ssw_test", ["-c", "-s", "target.fastq", "query.fastq"]),
     ("ssw_test", ["-m", "1", "-x", "3", "-o", "5", "-e", "2", "-c", "1k.fa", "54mer_hap1_1.100.fa"]),
+    ("ssw_test", ["-a", "b62.txt", "-c", "protein2.fa", "protein1.fa"]),        # weight matrix file
+    ("ssw_test", ["-c", "-s", "-r", "-h", "1k.fa", "54mer_hap1_1.100.fastq"]),        # SAM, both strands, qualities
+    ("ssw_test", ["-c", "-r", "-f", "60", "1k.fa", "54mer_hap1_1.100.fa"]),           # score filter
+    ("ssw_test", ["-r", "1k.fa", "54mer_hap1_1.100.fa"]),                             # scores only, both strands
     ("example_c", []),
     ("example_cpp", []),
 ]:
-    a = [x if not x.endswith((".fa", ".fq", ".fastq")) else os.path.join(DEMO, x) for x in args]
-    out = subprocess.run([os.path.join(BIN, exe + "_ref")] + a, capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([os.path.join(BIN, exe + "_ref")] + args, capture_output=True, text=True, check=True, cwd=TMP).stdout
     out = "\n".join(l for l in out.splitlines() if not l.startswith("CPU time"))
     runs.append({"exe": exe, "args": args, "stdout": out})
 

@@ -311,7 +311,26 @@ def test_unmodified_reference_consumers_on_our_library(tmp_path, capfd):
         (tmp_path / name).write_text(seqs)
     for run in G["runs"]:
         exe = os.path.join(bindir, run["exe"] + "_b200")
-        args = [a if not a.endswith((".fa", ".fq", ".fastq")) else str(tmp_path / a) for a in run["args"]]
-        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+        out = subprocess.run([exe] + run["args"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
         got = "\n".join(l for l in out.stdout.splitlines() if not l.startswith("CPU time"))
         assert got == run["stdout"], (run["exe"], run["args"])
+
+
+def test_batch_cli_matches_reference_driver(tmp_path):
+    """ssw_batch_cli (one ssw_align_batch call for all read x reference x strand pairs) prints, byte for byte, what the
+    reference's ssw_test prints (main.c:129-244, :462-532) for the same command lines -- frozen in consumer_outputs.json."""
+    exe = os.path.join(C.PKG, "ssw_batch_cli")
+    assert os.path.exists(exe), "ssw_batch_cli not built (make -C complete-striped-smith-waterman-library_b200)"
+    with open(os.path.join(C.GOLDEN, "consumer_outputs.json")) as f:
+        G = json.load(f)
+    for name, seqs in G["files"].items():
+        (tmp_path / name).write_text(seqs)
+    n = 0
+    for run in G["runs"]:
+        if run["exe"] != "ssw_test":
+            continue
+        out = subprocess.run([exe] + run["args"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+        assert out.returncode == 0, out.stderr[-500:]
+        assert "\n".join(out.stdout.splitlines()) == run["stdout"], run["args"]
+        n += 1
+    assert n >= 10
