@@ -108,7 +108,13 @@ extern "C" int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
                                int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
                                s_align** out)
 {
-	if (!e || !params || !out) return -1;
+	if (!params || !out) return -1;
+	std::unique_lock<std::mutex> lock(g_mu, std::defer_lock);
+	if (!e) {                                   /* NULL: the process-wide engine that also serves ssw_align */
+		lock.lock();
+		e = default_engine();
+		if (!e) return -1;
+	}
 	if (params->mask_len >= 0 && params->mask_len < 15)
 		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
 	int rc = ssw_engine_set_sequences(e, n_queries, queries, query_off, n_refs, refs, ref_off);

@@ -81,6 +81,7 @@ int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 /*
  * Convenience: set_sequences + align + conversion to heap s_align records
  * (each to be released with align_destroy; NULL where ssw_align would return NULL).
+ * e == NULL selects the process-wide engine that serves ssw_align (created on first use, calls serialised).
  */
 int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
                     int32_t n_queries, const int8_t* queries, const int64_t* query_off,

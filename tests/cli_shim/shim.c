@@ -40,3 +40,17 @@ int32_t mark_mismatch(int32_t ref_begin1, int32_t read_begin1, int32_t read_end1
 {
 	return oracle_mark_mismatch(ref_begin1, read_begin1, read_end1, ref, read, readLen, cigar, cigarLen);
 }
+
+/* ssw.h entry points for the C++ wrapper's host-logic test */
+s_profile* ssw_init(const int8_t* read, const int32_t readLen, const int8_t* mat, const int32_t n, const int8_t score_size)
+{
+	return (s_profile*)oracle_ssw_init(read, readLen, mat, n, score_size);
+}
+void init_destroy(s_profile* p) { oracle_init_destroy((oracle_profile*)p); }
+s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t refLen, const uint8_t weight_gapO, const uint8_t weight_gapE,
+                   const uint8_t flag, const uint16_t filters, const int32_t filterd, const int32_t maskLen)
+{
+	return (s_align*)oracle_ssw_align((const oracle_profile*)prof, ref, refLen, weight_gapO, weight_gapE, flag, filters, filterd, maskLen);
+}
+
+const uint8_t encoded_ops[128] = { ['M'] = 0, ['I'] = 1, ['D'] = 2, ['N'] = 3, ['S'] = 4, ['H'] = 5, ['P'] = 6, ['='] = 7, ['X'] = 8 };

@@ -48,3 +48,16 @@ def test_library_exports_every_declared_symbol():
 def test_product_does_not_link_the_oracle():
     out = subprocess.run(["nm", "-D", C.LIB_OURS], capture_output=True, text=True).stdout
     assert "oracle_" not in out and "cuemu" not in out
+
+
+@pytest.mark.skipif(not os.path.exists(C.LIB_OURS), reason="libssw.so not built yet")
+def test_library_exports_the_cpp_wrapper():
+    """include/ssw_cpp.h: every public member of StripedSmithWaterman::Aligner is defined in libssw.so"""
+    out = subprocess.run(["nm", "-DC", "--defined-only", C.LIB_OURS], capture_output=True, text=True).stdout
+    for member in ("Aligner::Aligner()", "Aligner::SetReferenceSequence(char const*, unsigned long)",
+                   "Aligner::SetReferenceSequence(char const*)", "Aligner::ClearReferenceSequence()",
+                   "Aligner::SetGapPenalty(unsigned char, unsigned char)", "Aligner::Clear()", "Aligner::ReBuild()",
+                   "Aligner::AlignBatch(", "Aligner::Align(char const*, unsigned long, char const*, unsigned long,",
+                   "Aligner::Align(char const*, char const*,", "Aligner::Align(char const*, unsigned long, StripedSmithWaterman::Filter const&",
+                   "Aligner::Align(char const*, StripedSmithWaterman::Filter const&"):
+        assert "StripedSmithWaterman::" + member in out, member

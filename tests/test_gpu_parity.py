@@ -314,6 +314,10 @@ def test_unmodified_reference_consumers_on_our_library(tmp_path, capfd):
         out = subprocess.run([exe] + run["args"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
         got = "\n".join(l for l in out.stdout.splitlines() if not l.startswith("CPU time"))
         assert got == run["stdout"], (run["exe"], run["args"])
+        native = os.path.join(bindir, run["exe"] + "_native_b200")      # example.cpp over include/ssw_cpp.h
+        if os.path.exists(native):
+            out = subprocess.run([native], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+            assert "\n".join(out.stdout.splitlines()) == run["stdout"], native
 
 
 def test_batch_cli_matches_reference_driver(tmp_path):
@@ -334,3 +338,15 @@ def test_batch_cli_matches_reference_driver(tmp_path):
         assert "\n".join(out.stdout.splitlines()) == run["stdout"], run["args"]
         n += 1
     assert n >= 10
+
+
+def test_cpp_wrapper_matches_reference_wrapper(tmp_path):
+    """include/ssw_cpp.h + libssw.so (Align overloads, filters, ReBuild, custom alphabets, AlignBatch) print what the same
+    driver prints over the unmodified reference wrapper and ssw.c (tests/golden/cpp_wrapper.txt)."""
+    exe = str(tmp_path / "driver_gpu")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-DWITH_BATCH", "-I" + os.path.join(C.ROOT, "include"), "-o", exe,
+                    os.path.join(C.ROOT, "tests", "cpp_wrapper", "driver.cpp"), "-L" + C.PKG, "-lssw", "-Wl,-rpath," + C.PKG, "-lm"],
+                   check=True)
+    got = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert got.returncode == 0, got.stderr[-500:]
+    assert got.stdout == open(os.path.join(C.GOLDEN, "cpp_wrapper.txt")).read()
