@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--inst", type=int, default=-1, help="experiment: force a fill-kernel instance")
     ap.add_argument("--chunk", type=int, default=0, help="experiment: reference chunk length")
     ap.add_argument("--mode", type=int, default=-1, help="experiment: fill arithmetic (0 all-DPX, 1 biased + IMAD)")
+    ap.add_argument("--clock-sampler", choices=["smi", "nvml"], default="smi",
+                    help="how clocks / throttle reasons are sampled during the timed region")
     ap.add_argument("--lib", default="libssw.so", help="experiment: alternative build of the library")
     return ap.parse_args()
 
@@ -104,6 +106,54 @@ class ClockSampler:
                         reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class NvmlSampler:
+    """The same quantities read in-process through NVML (nvidia_ml_py) every 100 ms: no nvidia-smi process polling the
+    driver while the timed region runs (measured: the -lms 200 poller costs the timed steps several ms each)."""
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.h = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.idx
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml unavailable"}
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        seen = 0
+        for r in self.rows:
+            seen |= int(r[2])
+        return {"sm_mhz": float(np.median([r[0] for r in self.rows])), "sm_max_mhz": float(max(r[1] for r in self.rows)),
+                "reasons": sorted(k for k, b in bits.items() if seen & b), "samples": len(self.rows), "source": "nvml, 100 ms period"}
 
 
 def cpu_reference_rate(ref, reads, mat, n_threads, sample):
@@ -214,7 +264,7 @@ def main():
     eng.set_sequences(reads, [ref])
     for _ in range(args.warmup):
         gather(step_resident())
-    sampler = ClockSampler(local)
+    sampler = {"smi": ClockSampler, "nvml": NvmlSampler}[args.clock_sampler](local)
     if rank == 0:
         sampler.start()
     tot_ms = fill_ms = 0.0
