@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--inst", type=int, default=-1, help="experiment: force a fill-kernel instance")
     ap.add_argument("--chunk", type=int, default=0, help="experiment: reference chunk length")
     ap.add_argument("--mode", type=int, default=-1, help="experiment: fill arithmetic (0 all-DPX, 1 biased + IMAD)")
+    ap.add_argument("--opt", action="append", default=[], help="experiment: engine option name=value (repeatable)")
     ap.add_argument("--clock-sampler", choices=["smi", "nvml"], default="smi",
                     help="how clocks / throttle reasons are sampled during the timed region")
     ap.add_argument("--lib", default="libssw.so", help="experiment: alternative build of the library")
@@ -245,6 +246,9 @@ def main():
         eng.set_option("chunk", args.chunk)
     if args.mode >= 0:
         eng.set_option("mode", args.mode)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        eng.set_option(name, int(val))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
     def barrier():

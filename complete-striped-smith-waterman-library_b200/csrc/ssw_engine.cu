@@ -91,12 +91,14 @@ struct ssw_engine {
 	/* scratch */
 	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out;
 	int64_t opt_chunk = 0;
+	int64_t opt_small_chunk = 0;        /* experiment: chunk length of launches too small to fill the device */
 	ssw_engine_timing timing;
 	SswTimer t_total, t_k;
 
 	int upload_refs(int n);
 	int run_fill(const std::vector<SswItem>& items, int inst, int dir, int share, const ssw_batch_params& P, float* ms_acc);
 };
+
 
 /* ------------------------------------------------------------------------------------------- */
 /* fill kernel dispatch                                                                          */
@@ -253,6 +255,7 @@ extern "C" const char* ssw_engine_device_name(const ssw_engine* e) { return e ? 
 extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value)
 {
 	if (!e || !name) return -1;
+	if (!strcmp(name, "small_chunk")) { e->opt_small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "grid_min")) { g_grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
 	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }       /* index into kInst */
@@ -446,8 +449,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		std::vector<int64_t> desc_aln;
 		size_t cm_words = 0, bnd_words = 0, park_words = 0;
 		int n_best = 0;
-		size_t free_b = 0, total_b = 0;
-		cudaMemGetInfo(&free_b, &total_b);
+		const size_t free_b = ssw_free_device_bytes();
 		const size_t budget = std::max<size_t>((size_t)256 << 20, (free_b + e->d_bnd.cap + e->d_colmax.cap) / 2);
 		for (; k < order.size() && strips_of(reqs[order[k]]) == n_strips; ++k) {
 			const StripReq& q = reqs[order[k]];
@@ -614,8 +616,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 		pts.swap(ptmp);
 	}
 	tr.lap("forward: sort");
-	size_t free_b = 0, total_b = 0;
-	cudaMemGetInfo(&free_b, &total_b);
+	const size_t free_b = ssw_free_device_bytes();
 	const size_t cm_budget_words = std::max<size_t>((size_t)1 << 22, (free_b + e->d_colmax.cap) / 2 / 4);
 	tr.lap("forward: memgetinfo");
 
@@ -655,7 +656,8 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				if (P.gap_extend > 0 && S.max_mat > 0) {
 					warm = (int64_t)max_lp + ((int64_t)max_len * S.max_mat + P.gap_extend - 1) / P.gap_extend + 4;
 					warm = (warm + 3) / 4 * 4;
-					chunk = e->opt_chunk > 0 ? e->opt_chunk : std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
+					chunk = e->opt_chunk > 0 ? e->opt_chunk : (e->opt_small_chunk > 0 && base_chunk < 4096) ? std::max<int64_t>(e->opt_small_chunk, 2 * warm)
+					      : std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
 				}
 				int64_t n_chunks = chunk >= ref_len ? 1 : (ref_len + chunk - 1) / chunk;
 				if (n_chunks > 1 && e->opt_chunk == 0) {
@@ -821,8 +823,7 @@ static int emul_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>&
                      int word, int dir, const Sem& S)
 {
 	if (sel.empty()) return 0;
-	size_t free_b = 0, total_b = 0;
-	cudaMemGetInfo(&free_b, &total_b);
+	const size_t free_b = ssw_free_device_bytes();
 	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + e->d_emul.cap) / 2);
 	size_t k = 0;
 	while (k < sel.size()) {
@@ -934,8 +935,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 	SSW_CUDA_OK(cudaMemsetAsync(gb + o_cnt, 0, 256, e->stream));
 	if (e->d_out.ensure(sizeof(ssw_batch_result) * (size_t)n_pairs)) return -1;
 
-	size_t free_b = 0, total_b = 0;
-	cudaMemGetInfo(&free_b, &total_b);
+	const size_t free_b = ssw_free_device_bytes();
 	const size_t budget = std::max<size_t>((size_t)256 << 20, (free_b + e->d_colmax.cap + e->d_items.cap + e->d_alns.cap + e->d_res.cap) / 2);
 	tr.lap("grid: tables");
 	size_t k = 0;

@@ -398,8 +398,7 @@ static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
 		t.bw = t.init_bw = (d < 0 ? -d : d) + 1;                 /* ssw.c:944 */
 		t.max = 0; t.max_i = 0; t.max_j = 0; t.status = SSW_TB_WIDER; t.cig_len = 0;
 	}
-	size_t free_b = 0, total_b = 0;
-	cudaMemGetInfo(&free_b, &total_b);
+	const size_t free_b = ssw_free_device_bytes();
 	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + scratch->cap) / 2);
 	auto ring_of = [](const SswTbTask& t) -> int {          /* 0: single-warp kernel with global row buffers */
 		if (t.bw > g_ssw_tb_maxbw) return 0;

@@ -21,6 +21,7 @@ __device__ __forceinline__ uint32_t apply(uint32_t a, uint32_t b, uint32_t c, in
 	if (OP == 6) return __shfl_up_sync(0xffffffffu, a, 1);
 	if (OP == 7) return (a & b) ^ c;                     // LOP3
 	if (OP == 8) return a + b + c;                       // IADD3
+	if (OP == 9) { uint32_t d; asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }   // HMNMX2
 	return a;
 }
 
@@ -67,6 +68,33 @@ __global__ void probe_mix(uint32_t* out, long long* cyc, uint32_t seed)
 			for (int i = 0; i < NA; ++i) va[i] = __viaddmax_s16x2(va[i], va[(i + 1) % NA], va[(i + 3) % NA]);
 #pragma unroll
 			for (int i = 0; i < NB; ++i) vb[i] = vb[i] * b + c;
+		}
+	}
+	long long t1 = clock64();
+	uint32_t acc = 0;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) acc ^= va[i] ^ vb[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+	if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// mixed: NA DPX ops and NB packed-half maxima (HMNMX2, FMA-side pipe) per iteration on independent chains
+template <int NA, int NB>
+__global__ void probe_mix_h(uint32_t* out, long long* cyc, uint32_t seed)
+{
+	uint32_t va[8], vb[8];
+#pragma unroll
+	for (int i = 0; i < 8; ++i) { va[i] = seed * (i + 1) + threadIdx.x; vb[i] = (seed * (i + 9) + threadIdx.x) & 0x3fff3fffu; }
+	__syncthreads();
+	long long t0 = clock64();
+#pragma unroll 1
+	for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+#pragma unroll
+			for (int i = 0; i < NA; ++i) va[i] = __viaddmax_s16x2(va[i], va[(i + 1) % NA], va[(i + 3) % NA]);
+#pragma unroll
+			for (int i = 0; i < NB; ++i) { uint32_t d; asm volatile("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(vb[i]), "r"(vb[(i + 1) % NB])); vb[i] = d; }
 		}
 	}
 	long long t1 = clock64();
@@ -124,6 +152,11 @@ int main()
 			const double m44 = run(probe_mix<4, 4>, threads, 4 * 8, sms);
 			const double m62 = run(probe_mix<6, 2>, threads, 4 * 8, sms);
 			const double m80 = run(probe_mix<8, 0>, threads, 4 * 8, sms);
+			const double h80 = run(probe_mix_h<8, 0>, threads, 4 * 8, sms);
+			const double h62 = run(probe_mix_h<6, 2>, threads, 4 * 8, sms);
+			const double h44 = run(probe_mix_h<4, 4>, threads, 4 * 8, sms);
+			const double h08 = run(probe<9>, threads, 4 * ILP, sms);
+			printf(", \"mix_dpx_hmnmx2_1024thr\": {\"8+0\": %.3f, \"6+2\": %.3f, \"4+4\": %.3f, \"HMNMX2 alone\": %.3f}", h80, h62, h44, h08);
 			printf(", \"mix_dpx_imad_1024thr\": {\"4+4\": %.3f, \"6+2\": %.3f, \"8+0\": %.3f}", m44, m62, m80);
 			// fill kernel: 5.5 DPX ops per lane per two cells -> cells/clk/SM = rate * 32 lanes * 2 / 5.5
 			const double cells_per_clk_sm = r[0] * 32.0 * 2.0 / 5.5;
