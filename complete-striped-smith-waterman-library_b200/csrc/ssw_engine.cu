@@ -1034,6 +1034,7 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 {
 	/* gapO <= gapE: the reference's result depends on its SIMD layout (lazy-F exit); use the lane-literal kernel */
 	const bool literal = P.gap_open <= P.gap_extend;
+	Trace phase;
 
 	std::vector<Aln> alns((size_t)n_pairs);
 	for (int64_t p = 0; p < n_pairs; ++p) {
@@ -1097,6 +1098,7 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 		if (!literal && a.word == 1 && S.has_byte && a.fwd.score >= S.limit_byte) e->timing.byte_overflows += 1;
 	}
 
+	phase.lap("general: forward passes");
 	/* ---- gating (ssw.c:900-916) and P2 ---- */
 	std::vector<int64_t> need_begin;
 	for (int64_t p = 0; p < n_pairs; ++p) {
@@ -1115,6 +1117,7 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 		if (rc) return rc;
 	}
 
+	phase.lap("general: reverse passes");
 	/* ---- assemble the fixed-size records ---- */
 	std::vector<uint8_t> has_begin((size_t)n_pairs, 0);
 	for (int64_t p : need_begin) has_begin[p] = 1;
@@ -1155,6 +1158,7 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 		tb_pair.push_back(p);
 	}
 
+	phase.lap("general: records");
 	/* ---- P3 ---- */
 	if (!tb.empty()) {
 		rc = ssw_traceback_run(e->stream, tb, e->d_q.as<int8_t>(), e->d_r.as<int8_t>(), e->d_mat.as<int8_t>(), P.n,
@@ -1170,6 +1174,7 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 		});
 		if (rc) return rc;
 	}
+	phase.lap("general: traceback");
 	return 0;
 }
 

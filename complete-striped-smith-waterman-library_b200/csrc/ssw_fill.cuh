@@ -153,7 +153,7 @@ __device__ static __forceinline__ void ssw_load_scores(uint32_t (&s)[R], ssw_sad
 template <int R>
 __device__ static __forceinline__ void ssw_cells(uint32_t (&Hd)[R], uint32_t (&E)[R], const uint32_t (&s)[R], uint32_t (&Hn)[R],
                                                 uint32_t inH, uint32_t inF, uint32_t inC, uint32_t negO, uint32_t negE,
-                                                uint32_t& outH, uint32_t& outF, uint32_t& outC)
+                                                uint32_t& outH, uint32_t& outF, uint32_t& outC, uint32_t& own)
 {
 	uint32_t F = inF;
 #pragma unroll
@@ -164,12 +164,20 @@ __device__ static __forceinline__ void ssw_cells(uint32_t (&Hd)[R], uint32_t (&E
 		Hn[k] = __vmaxs2(X, F);
 		F = __viaddmax_s16x2(F, negE, Xg);
 	}
-	/* partial column maximum: the value handed down from the lanes above, folded with this lane's rows */
-	uint32_t m = inC;
+	/* `own`: maximum of the column over this lane's rows (the best-cell bookkeeping compares it with the lane's running
+	 * best); outC: the partial column maximum handed down the lanes, own folded with the value from above */
+	uint32_t m;
+	if (R >= 3) {
+		m = __vimax3_s16x2(Hn[0], Hn[1], Hn[2]);
 #pragma unroll
-	for (int k = 0; k + 1 < R; k += 2) m = __vimax3_s16x2(m, Hn[k], Hn[k + 1]);
-	if (R & 1) m = __vmaxs2(m, Hn[R - 1]);
-	outC = m;
+		for (int k = 3; k + 1 < R; k += 2) m = __vimax3_s16x2(m, Hn[k], Hn[k + 1]);
+		if (((R - 3) & 1) != 0) { own = __vmaxs2(m, Hn[R - 1]); outC = __vmaxs2(own, inC); }
+		else { own = m; outC = __vmaxs2(m, inC); }
+	} else {
+		m = Hn[0];
+		if (R == 2) m = __vmaxs2(m, Hn[1]);
+		own = m; outC = __vmaxs2(m, inC);
+	}
 	Hd[0] = inH;
 #pragma unroll
 	for (int k = 1; k < R; ++k) Hd[k] = Hn[k - 1];
@@ -204,21 +212,18 @@ __device__ static __forceinline__ void ssw_snap_pin(SswSnap<R>& sn)
 }
 
 template <int R>
-__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, SswSnap<R>& sn, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1,
-                                                uint32_t floor2)
+__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, SswSnap<R>& sn, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1)
 {
 #ifndef SSW_CPU_EMU
 	asm volatile("" : "+r"(sp));                /* keep the range test inside this rare path */
 #endif
 	if (sp >= p0 && sp < p1) {
-		/* `floor2` is a lower bound of the group's final maximum (the group maximum of a few steps ago): an increase
-		 * that stays below it can never be the best cell, so it need not be recorded */
-		if (half_of(nb, 0) > half_of(lb.best, 0) && half_of(nb, 0) >= half_of(floor2, 0)) {
+		if (half_of(nb, 0) > half_of(lb.best, 0)) {
 			lb.pos0 = sp;
 #pragma unroll
 			for (int k = 0; k < R; ++k) sn.w[0][k] = Hn[k];
 		}
-		if (half_of(nb, 1) > half_of(lb.best, 1) && half_of(nb, 1) >= half_of(floor2, 1)) {
+		if (half_of(nb, 1) > half_of(lb.best, 1)) {
 			lb.pos1 = sp;
 #pragma unroll
 			for (int k = 0; k < R; ++k) sn.w[1][k] = Hn[k];
@@ -344,10 +349,14 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	SswSnap<R> snap;
 	ssw_snap_pin<R>(snap);
 
-	uint32_t floor2 = 0;                                /* lower bound of the group's final maximum, refreshed every 4 bodies */
 	for (int body = 0; body < n_body; ++body) {
 		uint32_t cmv[U];
-		if ((body & 3) == 0) floor2 = ssw_group_max<G>(lb.best);
+		if ((body & 1) == 0) {
+			/* lower bound of the group's final maximum: a lane value below it can never be the best cell, so the lane's
+			 * running best is raised to (bound - 1) and such values no longer trigger the bookkeeping */
+			const uint32_t floor2 = ssw_group_max<G>(lb.best);
+			lb.best = __vmaxs2(lb.best, __vadd2(floor2, 0xffffffffu));
+		}
 		const bool maybe_counted = sp0 + U - 1 >= it.p0 && sp0 < it.p1;   /* this body touches the counted range */
 #pragma unroll
 		for (int j = 0; j < U; ++j) {
@@ -361,12 +370,13 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 			if (DIR < 0) { if (sp0 + j < 0) letter = n; }
 			uint32_t s[R], Hn[R];
 			ssw_load_scores<R>(s, pbase, ptail, letter);
-			ssw_cells<R>(Hd, E, s, Hn, inH, inF, inC, negO, negE, outH, outF, outC);
+			uint32_t own;
+			ssw_cells<R>(Hd, E, s, Hn, inH, inF, inC, negO, negE, outH, outF, outC, own);
 			cmv[j] = outC;
 
-			/* running best of this lane (strict increase only; rare path) */
-			const uint32_t nb = __vmaxs2(lb.best, outC);
-			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, it.p0, it.p1, floor2);
+			/* running best of this lane's rows (strict increase only; rare path) */
+			const uint32_t nb = __vmaxs2(lb.best, own);
+			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, it.p0, it.p1);
 		}
 
 		if (WRITE_CM) {
@@ -555,10 +565,11 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 					if (sp0 + j < 0) letter = n;                    /* before the scan start (reverse: right of cend) */
 					uint32_t sc[R], Hn[R];
 					ssw_load_scores<R>(sc, pbase, ptail, letter);
-					ssw_cells<R>(Hd, E, sc, Hn, inH, inF, inC, negO, negE, outH, outF, outC);
+					uint32_t own;
+					ssw_cells<R>(Hd, E, sc, Hn, inH, inF, inC, negO, negE, outH, outF, outC, own);
 					cmv[j] = outC; hv[j] = outH; fv[j] = outF;
-					const uint32_t nb = __vmaxs2(lb.best, outC);
-					if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, 0, T.p1, 0u);
+					const uint32_t nb = __vmaxs2(lb.best, own);
+					if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, 0, T.p1);
 				}
 				/* the last lane publishes the strip's bottom row (the last strip: the column maxima) */
 				if (lane == 31 && sL >= 0) {

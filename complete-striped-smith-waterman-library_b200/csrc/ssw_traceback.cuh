@@ -150,6 +150,102 @@ __device__ static __forceinline__ void ssw_tb_tile(bool act, int i, int j, int b
 	carryF = max(P31, carryF - 32 * g);
 }
 
+/* NT adjacent tiles of one band row at once.  Same arithmetic as ssw_tb_tile, reordered so that the tiles' scans
+ * (the long chain of dependent shuffles) are independent instruction streams the scheduler can interleave; only the
+ * F carry from tile to tile is serial, and that is one max per tile.  A row of the band then costs about one tile's
+ * latency instead of NT. */
+template <int NT>
+__device__ static __forceinline__ void ssw_tb_tiles(const bool (&act)[NT], int i, const int (&j)[NT], int beg, int lane,
+                                                   const int (&Hup)[NT], const int (&Eup)[NT], const int (&Hdg)[NT], const int (&s)[NT],
+                                                   int gapO, int gapE, int g, int& carryF, int& carryH, int& carryFp,
+                                                   int (&Hv)[NT], int (&Ev)[NT], int (&dirb)[NT])
+{
+	constexpr unsigned FULL = 0xffffffffu;
+	int de3[NT], e1[NT], T2[NT], Y[NT], P[NT];
+#pragma unroll
+	for (int t = 0; t < NT; ++t) {
+		const int t1 = i == 0 ? -gapO : Hup[t] - gapO;
+		const int t2 = i == 0 ? SSW_TB_NEGINF : Eup[t] - gapE;
+		Ev[t] = t1 > t2 ? t1 : t2;
+		de3[t] = t1 > t2 ? 1 : 0;
+		e1[t] = Ev[t] > 0 ? Ev[t] : 0;
+		T2[t] = Hdg[t] + s[t];
+		Y[t] = e1[t] > T2[t] ? e1[t] : T2[t];
+		P[t] = act[t] ? Y[t] - gapO : SSW_TB_NEGINF;
+	}
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+		for (int t = 0; t < NT; ++t) {
+			const int o = __shfl_up_sync(FULL, P[t], d);
+			if (lane >= d) P[t] = max(P[t], o - d * g);
+		}
+	}
+	int Pm1[NT], P31[NT], cF[NT], Fv[NT];
+#pragma unroll
+	for (int t = 0; t < NT; ++t) { Pm1[t] = __shfl_up_sync(FULL, P[t], 1); P31[t] = __shfl_sync(FULL, P[t], 31); }
+	cF[0] = carryF;
+#pragma unroll
+	for (int t = 1; t < NT; ++t) cF[t] = max(P31[t - 1], cF[t - 1] - 32 * g);
+	carryF = max(P31[NT - 1], cF[NT - 1] - 32 * g);
+	int H31[NT], F31[NT], Hl[NT], Fl[NT];
+#pragma unroll
+	for (int t = 0; t < NT; ++t) {
+		Fv[t] = lane == 0 ? cF[t] : max(Pm1[t], cF[t] - lane * g);
+		Hv[t] = Y[t] > Fv[t] ? Y[t] : Fv[t];
+		H31[t] = __shfl_sync(FULL, Hv[t], 31);
+		F31[t] = __shfl_sync(FULL, Fv[t], 31);
+		Hl[t] = __shfl_up_sync(FULL, Hv[t], 1);
+		Fl[t] = __shfl_up_sync(FULL, Fv[t], 1);
+	}
+#pragma unroll
+	for (int t = 0; t < NT; ++t) {
+		if (lane == 0) { Hl[t] = t == 0 ? carryH : H31[t - 1]; Fl[t] = t == 0 ? carryFp : F31[t - 1]; }
+		const int df5 = j[t] == beg ? 1 : ((Hl[t] - gapO > Fl[t] - gapE) ? 1 : 0);
+		const int f1 = Fv[t] > 0 ? Fv[t] : 0;
+		const int T1 = e1[t] > f1 ? e1[t] : f1;
+		const int hsel = T1 <= T2[t] ? 0 : (e1[t] > f1 ? 1 : 2);
+		dirb[t] = de3[t] | (df5 << 1) | (hsel << 2);
+	}
+	carryH = H31[NT - 1];
+	carryFp = F31[NT - 1];
+}
+
+/* one group of NT tiles of row i starting at column j0: loads from the row ring, ssw_tb_tiles, stores */
+template <int NT>
+__device__ static __forceinline__ void ssw_tb_row_group(int i, int j0, int beg, int end, int pbeg, bool top_oob, int lane, int rd,
+                                                       const int32_t* Hprev, const int32_t* Eprev, int32_t* Hcur, int32_t* Ecur, int mask,
+                                                       const int8_t* smat, int n, const int8_t* ref, uint8_t* drow,
+                                                       int gapO, int gapE, int g, int& carryF, int& carryH, int& carryFp,
+                                                       int& bestv, int& besti, int& bestj)
+{
+	bool act[NT];
+	int j[NT], Hup[NT], Eup[NT], Hdg[NT], s[NT], Hv[NT], Ev[NT], dirb[NT];
+#pragma unroll
+	for (int t = 0; t < NT; ++t) {
+		j[t] = j0 + 32 * t + lane;
+		act[t] = j[t] <= end;
+		Hup[t] = 0; Eup[t] = SSW_TB_NEGINF; Hdg[t] = 0; s[t] = 0;
+		if (act[t]) {
+			if (i > 0) {
+				if (!(j[t] == end && top_oob)) { Hup[t] = Hprev[j[t] & mask]; Eup[t] = Eprev[j[t] & mask]; }
+				if (j[t] - 1 >= pbeg) Hdg[t] = Hprev[(j[t] - 1) & mask];
+			}
+			s[t] = (int)smat[(int)ref[j[t]] * n + rd];
+		}
+	}
+	ssw_tb_tiles<NT>(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryH, carryFp, Hv, Ev, dirb);
+#pragma unroll
+	for (int t = 0; t < NT; ++t) {
+		if (act[t]) {
+			Hcur[j[t] & mask] = Hv[t];
+			Ecur[j[t] & mask] = Ev[t];
+			drow[j[t]] = (uint8_t)dirb[t];
+			if (Hv[t] > bestv) { bestv = Hv[t]; besti = i; bestj = j[t]; }
+		}
+	}
+}
+
 /*
  * Fast variant for bands up to SSW_TBP_MAXBW: one warp per alignment, four alignments per CTA.  The two live H/E
  * rows sit in shared memory (indexed by reference column modulo the ring width), the scoring matrix too, so a
@@ -204,24 +300,21 @@ ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
 			uint8_t* drow = dir + (size_t)W * i - beg;
 			{
 				int carryF = -gapO, carryH = 0, carryFp = 0;
-				for (int j0 = beg; j0 <= end; j0 += 32) {
-					const int j = j0 + lane;
-					const bool act = j <= end;
-					int Hup = 0, Eup = SSW_TB_NEGINF, Hdg = 0, s = 0;
-					if (act) {
-						if (i > 0) {
-							if (!(j == end && top_oob)) { Hup = Hrow[prv][j & mask]; Eup = Erow[prv][j & mask]; }
-							if (j - 1 >= pbeg) Hdg = Hrow[prv][(j - 1) & mask];
-						}
-						s = (int)smat[(int)ref[j] * n + rd];
-					}
-					int Hv, Ev, dirb;
-					ssw_tb_tile(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryH, carryFp, Hv, Ev, dirb);
-					if (act) {
-						Hrow[cur][j & mask] = Hv;
-						Erow[cur][j & mask] = Ev;
-						drow[j] = (uint8_t)dirb;
-						if (Hv > bestv) { bestv = Hv; besti = i; bestj = j; }
+				int j0 = beg;
+				while (j0 <= end) {
+					const int tiles = (end - j0) / 32 + 1;
+					if (tiles >= 3) {
+						ssw_tb_row_group<4>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
+						                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
+						j0 += 128;
+					} else if (tiles == 2) {
+						ssw_tb_row_group<2>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
+						                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
+						j0 += 64;
+					} else {
+						ssw_tb_row_group<1>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
+						                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
+						j0 += 32;
 					}
 				}
 			}
@@ -384,6 +477,19 @@ ssw_banded_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
  * as long as its slowest task and overlapping the groups hides most of that.  `emit(i, words, len, failed)` is
  * called once per task with the final CIGAR (failed != 0: banded_sw gave up -> flag 1).
  */
+/* finished CIGARs -> one dense array (the per-task buffers are sized for the worst case, ref_len + read_len words):
+ * task i's words move from cig[cig_off ...] to dense[row_off ...]; row_off is re-used as the destination offset */
+__global__ void __launch_bounds__(128)
+ssw_cigar_pack_kernel(const SswTbTask* __restrict__ tasks, int n_tasks, const uint32_t* __restrict__ cig, uint32_t* __restrict__ dense)
+{
+	const int ti = (int)blockIdx.x;
+	if (ti >= n_tasks) return;
+	const int len = tasks[ti].status == SSW_TB_OK ? tasks[ti].cig_len : 0;
+	const uint32_t* src = cig + tasks[ti].cig_off;
+	uint32_t* dst = dense + tasks[ti].row_off;
+	for (int k = (int)threadIdx.x; k < len; k += (int)blockDim.x) dst[k] = src[k];
+}
+
 static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
                              const int8_t* d_q, const int8_t* d_r, const int8_t* d_mat, int n, int gapO, int gapE,
                              SswDevBuf* scratch, float* ms_acc, int64_t* launches,
@@ -473,9 +579,35 @@ static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
 		for (int si = 0; si < 3 && si < n_groups - 1; ++si) SSW_CUDA_OK(cudaStreamSynchronize(side[si]));
 		*ms_acc += tm.stop(stream);
 		SSW_CUDA_OK(cudaMemcpyAsync(bt.data(), d_tasks, sizeof(SswTbTask) * bt.size(), cudaMemcpyDeviceToHost, stream));
-		cig_host.resize(cig_words);
-		SSW_CUDA_OK(cudaMemcpyAsync(cig_host.data(), base + off_cig, cig_words * 4, cudaMemcpyDeviceToHost, stream));
 		SSW_CUDA_OK(cudaStreamSynchronize(stream));
+		/* bring back only the words the finished paths use: pack them densely into the (now free) direction area */
+		std::vector<int64_t> dense_off(bt.size(), 0);
+		size_t dense_words = 0;
+		{
+			std::vector<SswTbTask> pk(bt);
+			for (size_t i = 0; i < pk.size(); ++i) {
+				dense_off[i] = (int64_t)dense_words;
+				pk[i].row_off = (int64_t)dense_words;
+				if (pk[i].status == SSW_TB_OK) dense_words += (size_t)pk[i].cig_len;
+			}
+			if (dense_words * 4 > off_rows) {
+				/* (pathological paths with a run per base) no room to pack: copy the worst-case buffers as they are */
+				for (size_t i = 0; i < bt.size(); ++i) dense_off[i] = bt[i].cig_off;
+				cig_host.resize(cig_words + 1);
+				SSW_CUDA_OK(cudaMemcpyAsync(cig_host.data(), base + off_cig, cig_words * 4, cudaMemcpyDeviceToHost, stream));
+				SSW_CUDA_OK(cudaStreamSynchronize(stream));
+				dense_words = 0;
+			} else cig_host.resize(dense_words + 1);
+			if (dense_words > 0) {
+				SSW_CUDA_OK(cudaMemcpyAsync(d_tasks, pk.data(), sizeof(SswTbTask) * pk.size(), cudaMemcpyHostToDevice, stream));
+				ssw_launch(ssw_cigar_pack_kernel, dim3((unsigned)pk.size()), dim3(128), 0, stream, (const SswTbTask*)d_tasks, (int)pk.size(),
+				           (const uint32_t*)d_cig, reinterpret_cast<uint32_t*>(base));
+				SSW_CUDA_OK(cudaGetLastError());
+				*launches += 1;
+				SSW_CUDA_OK(cudaMemcpyAsync(cig_host.data(), base, dense_words * 4, cudaMemcpyDeviceToHost, stream));
+				SSW_CUDA_OK(cudaStreamSynchronize(stream));
+			}
+		}
 		if (getenv("SSW_TRACE")) {
 			double f = 0, w = 0, s = 0; int nf = 0; long long fmax = 0, wmax = 0;
 			for (const SswTbTask& x : bt) { f += (double)x.dbg_fill; fmax = std::max<long long>(fmax, x.dbg_fill); if (x.dbg_walk) { w += (double)x.dbg_walk; s += (double)x.dbg_score; wmax = std::max<long long>(wmax, x.dbg_walk); ++nf; } }
@@ -488,7 +620,7 @@ static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
 			t = bt[i];
 			const int full = t.ref_len > t.read_len ? t.ref_len : t.read_len;
 			if (t.status == SSW_TB_WIDER) { t.bw *= 2; next.push_back(batch[i]); }
-			else if (t.status == SSW_TB_OK) { if (emit(batch[i], cig_host.data() + t.cig_off, t.cig_len, 0)) return -1; }
+			else if (t.status == SSW_TB_OK) { if (emit(batch[i], cig_host.data() + dense_off[i], t.cig_len, 0)) return -1; }
 			else if (t.status == SSW_TB_ERROR) { if (emit(batch[i], nullptr, 0, 1)) return -1; }
 			else {                                                /* score mismatch: one retry at full band (ssw.c:952-956) */
 				if (t.init_bw >= full) { if (emit(batch[i], nullptr, 0, 1)) return -1; }

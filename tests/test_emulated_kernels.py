@@ -194,3 +194,34 @@ def test_emulated_device_planned_grid(oracle, capfd):
             assert n_over > 0          # the high-identity 150-mers overflow 8-bit scores
     eng.set_option("grid_min", -1)
     eng.close()
+
+
+def test_emulated_wide_bands_multi_tile(oracle, capfd):
+    """Traceback bands of several 32-column tiles per row (long deletions / insertions): the multi-tile row groups of
+    the shared-memory kernel (4-, 2- and 1-tile groups), band doubling inside the kernel, and the global-memory kernel."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    rng = np.random.default_rng(2718)
+    mat = C.dna_matrix(2, 2)
+    ref = rng.integers(0, 4, size=1600).astype(np.int8)
+    ins = rng.integers(0, 4, size=70).astype(np.int8)
+    reads = [
+        np.concatenate([ref[100:330], ref[450:700]]),            # 120-base deletion: band 121 -> 8 tiles per row
+        np.concatenate([ref[800:950], ins, ref[950:1150]]),      # 70-base insertion
+        np.concatenate([ref[200:300], ref[345:520]]),            # 45-base deletion: 3 tiles
+        C.mutate_read(rng, ref, 900, 260, 0.05, 0.03, 0.03),
+    ]
+    eng.set_sequences(reads, [ref])
+    for tb in (-1, 0):
+        eng.set_option("tb_maxbw", tb)
+        res, pool = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=60, score_size=2)
+        for i, q in enumerate(reads):
+            exp = oracle.align(q, ref, mat, 5, 3, 1, 0x0f, 0, 32767, 60, 2)
+            r = res[i]
+            got = {k: int(r[k]) for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
+            got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
+            assert C.diff_results(got, exp) == [], (tb, i)
+            assert len(got["cigar"]) >= 1
+    eng.set_option("tb_maxbw", -1)
+    eng.close()

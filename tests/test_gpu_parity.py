@@ -350,3 +350,28 @@ def test_cpp_wrapper_matches_reference_wrapper(tmp_path):
     got = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert got.returncode == 0, got.stderr[-500:]
     assert got.stdout == open(os.path.join(C.GOLDEN, "cpp_wrapper.txt")).read()
+
+
+def test_concurrent_callers(ours, checker, capfd):
+    """ssw_align is called from several host threads at once (the reference is re-entrant, SURVEY 8(b) Threading; ours
+    serialises the calls on the process-wide engine): every caller gets its own, correct record."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(31337)
+    mat = C.dna_matrix(2, 2)
+    cases = []
+    for _ in range(96):
+        ref = rng.integers(0, 4, size=int(rng.integers(200, 4000)), dtype=np.int8)
+        start = int(rng.integers(0, len(ref) - 120))
+        q = C.mutate_read(rng, ref, start, int(rng.integers(30, 110)), 0.08, 0.02, 0.02)
+        cases.append((q, ref, int(rng.choice([0, 1, 2, 8, 0x0f]))))
+
+    def run(c):
+        q, ref, flag = c
+        return ours.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, max(15, len(q) // 2), 2)
+
+    with ThreadPoolExecutor(8) as ex:
+        got = list(ex.map(run, cases))
+    for c, g in zip(cases, got):
+        q, ref, flag = c
+        exp = checker.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, max(15, len(q) // 2), 2)
+        assert C.diff_results(g, exp) == [], flag
