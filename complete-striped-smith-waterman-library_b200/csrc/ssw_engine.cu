@@ -422,6 +422,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
                       const std::function<int(std::vector<SswAlnDesc>&, const std::vector<int64_t>&)>& after)
 {
 	constexpr int R = SSW_STRIP_R;
+	Trace tr;
 	const int rows_per_strip = 32 * R;
 	const size_t warp_smem = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t);
 	/* one launch per distinct strip count (it fixes the CTA shape) */
@@ -484,14 +485,17 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 			n_best += n_strips * T.n_super;
 			tasks.push_back(T);
 		}
+		tr.lap("strips: plan");
 		if (e->d_items.ensure(sizeof(SswStripTask) * tasks.size())) return -1;
 		if (e->d_bests.ensure(sizeof(SswItemBest) * (size_t)n_best)) return -1;
 		if (e->d_colmax.ensure(cm_words * 4 + 64)) return -1;
 		if (e->d_bnd.ensure(bnd_words * 4 + 64)) return -1;
 		if (e->d_park.ensure(park_words * 4 + 64)) return -1;
+		tr.lap("strips: ensure");
 		SSW_CUDA_OK(cudaMemcpyAsync(e->d_items.p, tasks.data(), sizeof(SswStripTask) * tasks.size(), cudaMemcpyHostToDevice, e->stream));
 		SSW_CUDA_OK(cudaMemsetAsync(e->d_bests.p, 0, sizeof(SswItemBest) * (size_t)n_best, e->stream));
 		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 2);
+		tr.lap("strips: h2d + memset");
 		e->t_k.start(e->stream);
 #define SSW_STRIPS_GO(DIR, TERM)                                                                                        \
 		do {                                                                                                            \
@@ -507,8 +511,10 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		SSW_CUDA_OK(cudaGetLastError());
 		*ms_acc += e->t_k.stop(e->stream);
 		if (dir > 0) e->timing.fill_forward_launches += 1; else e->timing.other_launches += 1;
+		tr.lap("strips: kernel");
 		const int rc = after(descs, desc_aln);
 		if (rc) return rc;
+		tr.lap("strips: resolve + merge");
 	}
 	return 0;
 }
