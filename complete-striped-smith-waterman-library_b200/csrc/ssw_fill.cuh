@@ -527,6 +527,10 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 			if (DIR > 0) col = min(col, col_hi); else col = max(col, col_lo);
 			const uint8_t* lptr = rp + col;
 			bool stopped = false;
+			uint32_t top_keep = lane == 0 ? 0u : 1u;
+#ifndef SSW_CPU_EMU
+			asm volatile("" : "+r"(top_keep) : : "memory");     /* opaque 0/1 so that the masking stays a multiply */
+#endif
 
 			/* lane 0 is at scan position sL+31 .. sL+34 during a body: the last word of the aligned group at
 			 * sL+28 (carried from the previous body) and the first three of the group at sL+32 */
@@ -557,12 +561,13 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 				const bool maybe_counted = sp0 + 3 >= 0 && sp0 < T.p1;
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
-					uint32_t inH = __shfl_up_sync(FULL, outH, 1);
-					uint32_t inF = __shfl_up_sync(FULL, outF, 1);
-					uint32_t inC = __shfl_up_sync(FULL, outC, 1);
-					if (lane == 0) { inH = bHv[j]; inF = bFv[j]; inC = bCv[j]; }
+					/* lane 0 takes the boundary words (zero in the other lanes) instead of the shuffled ones: a multiply-add
+					 * by 0/1 on the FMA pipe rather than a select on the ALU pipe, which is the busy one */
+					const uint32_t inH = __shfl_up_sync(FULL, outH, 1) * top_keep + bHv[j];
+					const uint32_t inF = __shfl_up_sync(FULL, outF, 1) * top_keep + bFv[j];
+					const uint32_t inC = __shfl_up_sync(FULL, outC, 1) * top_keep + bCv[j];
 					int letter = (int)lptr[DIR * j];
-					if (sp0 + j < 0) letter = n;                    /* before the scan start (reverse: right of cend) */
+					if (DIR < 0) { if (sp0 + j < 0) letter = n; }   /* right of cend; forward scans start inside the null pad */
 					uint32_t sc[R], Hn[R];
 					ssw_load_scores<R>(sc, pbase, ptail, letter);
 					uint32_t own;
