@@ -53,6 +53,7 @@ static const Inst kInst[] = {
 static const int kNumFwd = 10;
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 
+static int g_strip_parts = 0;      /* "parts" option: 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
 static int g_strip_super = SSW_STRIP_SUPER;   /* columns per super-block of the strip kernel ("super" option, tests) */
 static int g_grid_min_pairs = 32768;    /* "grid_min" option: smaller grids use the general path */
 static int g_force_inst = -1;      /* experiment knob ("inst" option): use this instance whenever it covers the query */
@@ -89,7 +90,7 @@ struct ssw_engine {
 	SswDevBuf d_q, d_r, d_mat;
 
 	/* scratch */
-	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out;
+	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out, d_sync;
 	int64_t opt_chunk = 0;
 	int64_t opt_small_chunk = 0;        /* experiment: chunk length of launches too small to fill the device */
 	ssw_engine_timing timing;
@@ -244,7 +245,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 {
 	if (!e) return;
 	cudaSetDevice(e->device);
-	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out};
+	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out, &e->d_sync};
 	for (SswDevBuf* b : bufs) b->release();
 	if (e->stream) cudaStreamDestroy(e->stream);
 	delete e;
@@ -255,6 +256,7 @@ extern "C" const char* ssw_engine_device_name(const ssw_engine* e) { return e ? 
 extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value)
 {
 	if (!e || !name) return -1;
+	if (!strcmp(name, "parts")) { g_strip_parts = value == 1 || value == 2 || value == 4 ? (int)value : 0; return 0; }
 	if (!strcmp(name, "small_chunk")) { e->opt_small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "grid_min")) { g_grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
@@ -437,13 +439,34 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 	while (k < order.size()) {
 		const int n_strips = strips_of(reqs[order[k]]);
 		/* warps per CTA: as many as shared memory allows, preferring a count that divides the strips evenly */
-		int nw_max = (int)std::min<size_t>(SSW_STRIP_MAXW, (200 * 1024) / warp_smem);
-		if (nw_max < 1) { fprintf(stderr, "[libssw-b200] alphabet too large for the strip kernel\n"); return -2; }
-		nw_max = std::min(nw_max, n_strips);
-		int nw = nw_max; double best_eff = 0;
-		for (int w = nw_max; w >= 1; --w) {
-			const double eff = (double)n_strips / (double)(((n_strips + w - 1) / w) * w);
-			if (eff > best_eff + 1e-9) { best_eff = eff; nw = w; }
+		const int nw_cap = (int)std::min<size_t>(SSW_STRIP_MAXW, (200 * 1024) / warp_smem);
+		if (nw_cap < 1) { fprintf(stderr, "[libssw-b200] alphabet too large for the strip kernel\n"); return -2; }
+		/* Forward fills may split the strips of a task over `parts` CTAs (see the kernel).  One CTA per SM, every CTA of a
+		 * launch lasts about rounds x columns, so the launch lasts ceil(CTAs / SMs) x rounds: take the split that
+		 * minimises it (config 5: 500 tasks of 32 strips -> 4 waves x 2 rounds unsplit, 7 waves x 1 round in two parts). */
+		size_t n_same = 0;
+		for (size_t kk = k; kk < order.size() && strips_of(reqs[order[kk]]) == n_strips; ++kk) ++n_same;
+		int parts = 1, nw = 1;
+		{
+			double best_cost = 1e300;
+			const bool may_split = dir > 0 && !term && g_strip_parts != 1;
+			const bool forced = may_split && g_strip_parts > 1 && (n_strips + g_strip_parts - 1) / g_strip_parts >= 2;
+			for (int pp = 1; pp <= (may_split ? 4 : 1); pp *= 2) {
+				if (forced && pp != g_strip_parts) continue;
+				const int per = (n_strips + pp - 1) / pp;
+				if (pp > 1 && per < 2) break;
+				const int wmax = std::min(nw_cap, per);
+				int wbest = wmax; double eff_best = 0;
+				for (int w = wmax; w >= 1; --w) {
+					const double eff = (double)per / (double)(((per + w - 1) / w) * w);
+					if (eff > eff_best + 1e-9) { eff_best = eff; wbest = w; }
+				}
+				const double rounds = (double)((per + wbest - 1) / wbest);
+				const double waves = ceil((double)(n_same * pp) / (double)e->sm_count);
+				/* a CTA with few warps does not fill an SM: charge it as if it had at least 8 */
+				const double cost = waves * rounds * (wbest < 8 ? 8.0 / wbest : 1.0);
+				if (cost < best_cost - 1e-9) { best_cost = cost; parts = pp; nw = wbest; }
+			}
 		}
 		std::vector<SswStripTask> tasks;
 		std::vector<SswAlnDesc> descs;
@@ -494,6 +517,11 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		tr.lap("strips: ensure");
 		SSW_CUDA_OK(cudaMemcpyAsync(e->d_items.p, tasks.data(), sizeof(SswStripTask) * tasks.size(), cudaMemcpyHostToDevice, e->stream));
 		SSW_CUDA_OK(cudaMemsetAsync(e->d_bests.p, 0, sizeof(SswItemBest) * (size_t)n_best, e->stream));
+		/* ticket counter + one progress word per (task, part) */
+		std::vector<int> gsync(1 + tasks.size() * (size_t)parts, -0x40000000);
+		gsync[0] = 0;
+		if (e->d_sync.ensure(sizeof(int) * gsync.size())) return -1;
+		SSW_CUDA_OK(cudaMemcpyAsync(e->d_sync.p, gsync.data(), sizeof(int) * gsync.size(), cudaMemcpyHostToDevice, e->stream));
 		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 2);
 		tr.lap("strips: h2d + memset");
 		e->t_k.start(e->stream);
@@ -501,10 +529,10 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		do {                                                                                                            \
 			auto kern = ssw_fill_strips_kernel<SSW_STRIP_R, DIR, TERM>;                                                 \
 			if (smem > 48 * 1024) SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-			ssw_launch(kern, dim3((unsigned)tasks.size()), dim3(nw * 32), smem, e->stream, (const SswStripTask*)e->d_items.as<SswStripTask>(), \
+			ssw_launch(kern, dim3((unsigned)(tasks.size() * (size_t)parts)), dim3(nw * 32), smem, e->stream, (const SswStripTask*)e->d_items.as<SswStripTask>(), \
 			           (const int8_t*)e->d_q.as<int8_t>(), (const int8_t*)e->d_r.as<int8_t>(), (const int8_t*)e->d_mat.as<int8_t>(), (int)P.n, \
 			           (int)P.gap_open, (int)P.gap_extend, e->d_colmax.as<uint32_t>(), e->d_bnd.as<uint32_t>(), e->d_park.as<uint32_t>(), \
-			           e->d_bests.as<SswItemBest>());                                                                   \
+			           e->d_bests.as<SswItemBest>(), parts, e->d_sync.as<int>());                                       \
 		} while (0)
 		if (dir > 0) SSW_STRIPS_GO(1, false); else SSW_STRIPS_GO(-1, true);
 #undef SSW_STRIPS_GO

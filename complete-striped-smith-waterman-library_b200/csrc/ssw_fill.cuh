@@ -464,7 +464,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
                        const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
                        const int8_t* __restrict__ mat, int n, int gapO, int gapE,
                        uint32_t* __restrict__ colmax, uint32_t* bnd, uint32_t* park,
-                       SswItemBest* __restrict__ bests)
+                       SswItemBest* __restrict__ bests, int parts, int* gsync)
 {
 	constexpr int A4 = R / 4, REM = R % 4;
 	constexpr unsigned FULL = 0xffffffffu;
@@ -473,7 +473,23 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 
 	SSW_DYN_SMEM(uint32_t, smem);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-	const SswStripTask T = tasks[blockIdx.x];
+	/* parts > 1 (forward only): the strips of one task are split into `parts` contiguous blocks, one CTA each; the first
+	 * strip of a block follows the last strip of the previous block through a progress word in global memory.  Work is
+	 * handed out by a ticket, so the CTA a block waits for has always started (lower ticket): no dead-lock whatever the
+	 * order in which the hardware starts CTAs. */
+	int unit = (int)blockIdx.x;
+	if (parts > 1) {
+		__shared__ int s_ticket;
+		if (threadIdx.x == 0) s_ticket = atomicAdd(gsync, 1);
+		__syncthreads();
+		unit = s_ticket;
+	}
+	const int part = parts > 1 ? unit % parts : 0;
+	const SswStripTask T = tasks[parts > 1 ? unit / parts : unit];
+	const int per_part = (T.n_strips + parts - 1) / parts;
+	const int s_first = part * per_part, s_last = min(T.n_strips, s_first + per_part);      /* this CTA's strips [s_first, s_last) */
+	volatile int* gprog_in = gsync + 1 + (parts > 1 ? unit - 1 : 0);      /* published by the previous block of the same task */
+	volatile int* gprog_out = gsync + 1 + (parts > 1 ? unit : 0);
 	/* shared memory: NW profiles, then prog[n_strips], then the stop flag */
 	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
 	volatile int* prog = reinterpret_cast<volatile int*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R);
@@ -491,7 +507,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 	const int end = (T.p1 + 3) & ~3;                     /* last-lane positions run over [start, end) */
 
 	for (int sb = 0; sb < T.n_super; ++sb) {
-		for (int s = warp; s < T.n_strips; s += NW) {
+		for (int s = s_first + warp; s < s_last; s += NW) {
 			/* last-lane range [lo, hi) of this strip in this super-block */
 			const int lag = s * SSW_STRIP_LAG;
 			int lo = sb == 0 ? start : max(start, min(end, sb * T.super - lag));
@@ -527,6 +543,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 			if (DIR > 0) col = min(col, col_hi); else col = max(col, col_lo);
 			const uint8_t* lptr = rp + col;
 			bool stopped = false;
+			int known = -0x40000000;                            /* progress of the producing CTA as last read (s == s_first only) */
 			uint32_t top_keep = lane == 0 ? 0u : 1u;
 #ifndef SSW_CPU_EMU
 			asm volatile("" : "+r"(top_keep) : : "memory");     /* opaque 0/1 so that the masking stays a multiply */
@@ -545,8 +562,15 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 				if (lane == 0) {
 					if (s > 0) {
 						const int need = min(sL + 36, end);
-						while (prog[s - 1] < need && !(st = *stop)) { SSW_SPIN_PAUSE(); }
-						__threadfence_block();
+						if (s == s_first) {                          /* producer is another CTA: poll its global progress word */
+							if (known < need) {
+								while ((known = *gprog_in) < need) { SSW_SPIN_PAUSE(); }
+								__threadfence();
+							}
+						} else {
+							while (prog[s - 1] < need && !(st = *stop)) { SSW_SPIN_PAUSE(); }
+							__threadfence_block();
+						}
 						gH = ssw_ldcg(reinterpret_cast<const uint4*>(bin + sL + 32));
 						gF = ssw_ldcg(reinterpret_cast<const uint4*>(bin + T.bnd_len + sL + 32));
 						gC = ssw_ldcg(reinterpret_cast<const uint4*>(bin + 2 * T.bnd_len + sL + 32));
@@ -582,8 +606,13 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 						*reinterpret_cast<uint4*>(bout + sL) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
 						*reinterpret_cast<uint4*>(bout + T.bnd_len + sL) = make_uint4(fv[0], fv[1], fv[2], fv[3]);
 						*reinterpret_cast<uint4*>(bout + 2 * T.bnd_len + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
-						__threadfence_block();
-						prog[s] = sL + 4;
+						if (s + 1 == s_last) {
+							/* consumer in another CTA: device-scope fence, amortised over 32 columns (and the final ones) */
+							if (((sL + 4) & 31) == 0 || sL + 4 >= hi) { __threadfence(); *gprog_out = sL + 4; }
+						} else {
+							__threadfence_block();
+							prog[s] = sL + 4;
+						}
 					} else if (T.cm_off >= 0 && sL < T.p1) {
 						*reinterpret_cast<uint4*>(colmax + T.cm_off + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
 					}

@@ -94,15 +94,18 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
     mat = C.dna_matrix(2, 2)
     ref = rng.integers(0, 4, size=1800).astype(np.int8)
     reads = [C.mutate_read(rng, ref, int(rng.integers(0, 600)), n, 0.08, 0.02, 0.02) for n in (600, 1100, 530)]
+    reads.append(C.mutate_read(rng, np.concatenate([ref, ref[::-1]]), 100, 2100, 0.08, 0.02, 0.02))      # 7 strips: splits 4+3 and 2+2+2+1
     eng.set_sequences(reads, [ref])
-    for flag in (0, 0x0f):
+    for flag, parts in ((0, 0), (0x0f, 1), (0, 2), (0x0f, 2), (0, 4)):      # parts: strips of a task split over CTAs
+        eng.set_option("parts", parts)
         res, pool = eng.align(mat, 5, 3, 1, flag=flag, filterd=32767, mask_len=100, score_size=2)
         for i, q in enumerate(reads):
             exp = oracle.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, 100, 2)
             r = res[i]
             got = {k: int(r[k]) for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
             got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
-            assert C.diff_results(got, exp) == [], (flag, i)
+            assert C.diff_results(got, exp) == [], (flag, parts, i)
+    eng.set_option("parts", 0)
     eng.set_option("super", 0)
     eng.close()
 
