@@ -464,7 +464,8 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 				const double rounds = (double)((per + wbest - 1) / wbest);
 				const double waves = ceil((double)(n_same * pp) / (double)e->sm_count);
 				/* a CTA with few warps does not fill an SM: charge it as if it had at least 8 */
-				const double cost = waves * rounds * (wbest < 8 ? 8.0 / wbest : 1.0);
+				/* measured: a split CTA needs 8 % longer per round than an unsplit one (config 5: 32.7 vs 30.2 ms) */
+				const double cost = waves * rounds * (wbest < 8 ? 8.0 / wbest : 1.0) * (pp > 1 ? 1.08 : 1.0);
 				if (cost < best_cost - 1e-9) { best_cost = cost; parts = pp; nw = wbest; }
 			}
 		}
@@ -525,16 +526,17 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 2);
 		tr.lap("strips: h2d + memset");
 		e->t_k.start(e->stream);
-#define SSW_STRIPS_GO(DIR, TERM)                                                                                        \
+#define SSW_STRIPS_GO(DIR, TERM, SPLIT)                                                                                 \
 		do {                                                                                                            \
-			auto kern = ssw_fill_strips_kernel<SSW_STRIP_R, DIR, TERM>;                                                 \
+			auto kern = ssw_fill_strips_kernel<SSW_STRIP_R, DIR, TERM, SPLIT>;                                          \
 			if (smem > 48 * 1024) SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 			ssw_launch(kern, dim3((unsigned)(tasks.size() * (size_t)parts)), dim3(nw * 32), smem, e->stream, (const SswStripTask*)e->d_items.as<SswStripTask>(), \
 			           (const int8_t*)e->d_q.as<int8_t>(), (const int8_t*)e->d_r.as<int8_t>(), (const int8_t*)e->d_mat.as<int8_t>(), (int)P.n, \
 			           (int)P.gap_open, (int)P.gap_extend, e->d_colmax.as<uint32_t>(), e->d_bnd.as<uint32_t>(), e->d_park.as<uint32_t>(), \
 			           e->d_bests.as<SswItemBest>(), parts, e->d_sync.as<int>());                                       \
 		} while (0)
-		if (dir > 0) SSW_STRIPS_GO(1, false); else SSW_STRIPS_GO(-1, true);
+		if (dir > 0) { if (parts > 1) SSW_STRIPS_GO(1, false, true); else SSW_STRIPS_GO(1, false, false); }
+		else SSW_STRIPS_GO(-1, true, false);
 #undef SSW_STRIPS_GO
 		SSW_CUDA_OK(cudaGetLastError());
 		*ms_acc += e->t_k.stop(e->stream);

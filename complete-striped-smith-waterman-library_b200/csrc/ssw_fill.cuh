@@ -458,7 +458,24 @@ template <class T> __device__ static __forceinline__ T ssw_ldcg(const T* p) { re
 template <class T> __device__ static __forceinline__ T ssw_ldcg(const T* p) { return __ldcg(p); }
 #endif
 
-template <int R, int DIR, bool TERM>
+/* progress word shared by two CTAs: release store by the producer, acquire load by the consumer (device scope) */
+#ifdef SSW_CPU_EMU
+__device__ static __forceinline__ int ssw_ld_acquire(const volatile int* p) { return *p; }
+__device__ static __forceinline__ void ssw_st_release(volatile int* p, int v) { *p = v; }
+#else
+__device__ static __forceinline__ int ssw_ld_acquire(const volatile int* p)
+{
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ static __forceinline__ void ssw_st_release(volatile int* p, int v)
+{
+	asm volatile("st.release.gpu.global.s32 [%0], %1;" : : "l"(p), "r"(v) : "memory");
+}
+#endif
+
+template <int R, int DIR, bool TERM, bool SPLIT>
 __global__ void __launch_bounds__(SSW_STRIP_MAXW * 32)
 ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
                        const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
@@ -478,18 +495,18 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 	 * handed out by a ticket, so the CTA a block waits for has always started (lower ticket): no dead-lock whatever the
 	 * order in which the hardware starts CTAs. */
 	int unit = (int)blockIdx.x;
-	if (parts > 1) {
+	if (SPLIT) {
 		__shared__ int s_ticket;
 		if (threadIdx.x == 0) s_ticket = atomicAdd(gsync, 1);
 		__syncthreads();
 		unit = s_ticket;
 	}
-	const int part = parts > 1 ? unit % parts : 0;
-	const SswStripTask T = tasks[parts > 1 ? unit / parts : unit];
-	const int per_part = (T.n_strips + parts - 1) / parts;
+	const int part = SPLIT ? unit % parts : 0;
+	const SswStripTask T = tasks[SPLIT ? unit / parts : unit];
+	const int per_part = SPLIT ? (T.n_strips + parts - 1) / parts : T.n_strips;
 	const int s_first = part * per_part, s_last = min(T.n_strips, s_first + per_part);      /* this CTA's strips [s_first, s_last) */
-	volatile int* gprog_in = gsync + 1 + (parts > 1 ? unit - 1 : 0);      /* published by the previous block of the same task */
-	volatile int* gprog_out = gsync + 1 + (parts > 1 ? unit : 0);
+	volatile int* gprog_in = gsync + 1 + (SPLIT ? unit - 1 : 0);          /* published by the previous block of the same task */
+	volatile int* gprog_out = gsync + 1 + (SPLIT ? unit : 0);
 	/* shared memory: NW profiles, then prog[n_strips], then the stop flag */
 	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
 	volatile int* prog = reinterpret_cast<volatile int*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R);
@@ -543,7 +560,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 			if (DIR > 0) col = min(col, col_hi); else col = max(col, col_lo);
 			const uint8_t* lptr = rp + col;
 			bool stopped = false;
-			int known = -0x40000000;                            /* progress of the producing CTA as last read (s == s_first only) */
+			int known = -0x40000000, ahead = -0x40000000;       /* progress of the producing CTA as last read (s == s_first only) */
 			uint32_t top_keep = lane == 0 ? 0u : 1u;
 #ifndef SSW_CPU_EMU
 			asm volatile("" : "+r"(top_keep) : : "memory");     /* opaque 0/1 so that the masking stays a multiply */
@@ -562,11 +579,13 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 				if (lane == 0) {
 					if (s > 0) {
 						const int need = min(sL + 36, end);
-						if (s == s_first) {                          /* producer is another CTA: poll its global progress word */
-							if (known < need) {
-								while ((known = *gprog_in) < need) { SSW_SPIN_PAUSE(); }
-								__threadfence();
-							}
+						if (SPLIT && s == s_first) {
+							/* producer is another CTA: its progress word is read one loop body ahead of the need (the load
+							 * of the previous body has landed by now), so the wait loop is only entered when this strip has
+							 * really caught up with its producer */
+							known = max(known, ahead);
+							while (known < need) { SSW_SPIN_PAUSE(); known = ssw_ld_acquire(gprog_in); }
+							ahead = known < need + 160 ? ssw_ld_acquire(gprog_in) : known;
 						} else {
 							while (prog[s - 1] < need && !(st = *stop)) { SSW_SPIN_PAUSE(); }
 							__threadfence_block();
@@ -606,9 +625,9 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 						*reinterpret_cast<uint4*>(bout + sL) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
 						*reinterpret_cast<uint4*>(bout + T.bnd_len + sL) = make_uint4(fv[0], fv[1], fv[2], fv[3]);
 						*reinterpret_cast<uint4*>(bout + 2 * T.bnd_len + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
-						if (s + 1 == s_last) {
-							/* consumer in another CTA: device-scope fence, amortised over 32 columns (and the final ones) */
-							if (((sL + 4) & 31) == 0 || sL + 4 >= hi) { __threadfence(); *gprog_out = sL + 4; }
+						if (SPLIT && s + 1 == s_last) {
+							/* consumer in another CTA: device-scope release, amortised over 128 columns (and the final ones) */
+							if (((sL + 4) & 127) == 0 || sL + 4 >= hi) ssw_st_release(gprog_out, sL + 4);
 						} else {
 							__threadfence_block();
 							prog[s] = sL + 4;

@@ -19,10 +19,13 @@ ap.add_argument("--queries", type=int, default=64)
 ap.add_argument("--targets", type=int, default=50000)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--lib", default="libssw.so")
+ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
 ap.add_argument("--check", type=int, default=0, help="compare this many pairs with the reference/oracle")
 a = ap.parse_args()
 L = load_package()
 eng = L.BatchAligner(device=0, lib_name=a.lib)
+for kv in a.opt:
+    eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 if a.config == 5:
     ref, reads = C.make_dna_workload(100_000, a.reads, 10_000, seed_ref=5005, seed_reads=5006, decoy_frac=0.0, p_sub=0.05, p_ins=0.02, p_del=0.02)
     mat, n, flag, ml, ss = C.dna_matrix(2, 2), 5, (2 if a.flag < 0 else a.flag), 5000, 2
