@@ -91,6 +91,7 @@ struct ssw_engine {
 
 	/* scratch */
 	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out, d_sync;
+	SswStagedD2H staged;
 	int64_t opt_chunk = 0;
 	int64_t opt_small_chunk = 0;        /* experiment: chunk length of launches too small to fill the device */
 	ssw_engine_timing timing;
@@ -247,6 +248,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 	cudaSetDevice(e->device);
 	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out, &e->d_sync};
 	for (SswDevBuf* b : bufs) b->release();
+	e->staged.release();
 	if (e->stream) cudaStreamDestroy(e->stream);
 	delete e;
 }
@@ -261,7 +263,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "grid_min")) { g_grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
 	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }       /* index into kInst */
-	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 3) / 4 * 4 : SSW_STRIP_SUPER; return 0; }
+	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 7) / 8 * 8 : SSW_STRIP_SUPER; return 0; }
 	if (!strcmp(name, "tb_maxbw")) { g_ssw_tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
 	if (!strcmp(name, "mode")) return 0;      /* retired experiment (biased arithmetic with IMAD adds was slower, profiles/fill_kernel_r1.md) */
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
@@ -485,14 +487,14 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 			T.n_strips = n_strips;
 			T.super = g_strip_super;
 			T.n_super = term ? std::max(1, (q.p1 + T.super - 1) / T.super) : 1;
-			T.bnd_len = ((q.p1 + 3) / 4 * 4) + 2 * SSW_STRIP_BPAD + 64;
+			T.bnd_len = ((q.p1 + 7) / 8 * 8) + 2 * SSW_STRIP_BPAD + 64;
 			const size_t need = 4 * (cm_words + bnd_words + park_words + 6 * (size_t)T.bnd_len + (size_t)q.p1 + 8);
 			if (!tasks.empty() && need > budget) break;
 			T.cm_off = dir > 0 ? (int64_t)cm_words : -1;
 			T.bnd_off = (int64_t)bnd_words;
 			T.park_off = (int64_t)park_words;
 			T.first_best = n_best;
-			if (dir > 0) cm_words += ((size_t)q.p1 + 3) / 4 * 4 + 4;
+			if (dir > 0) cm_words += ((size_t)q.p1 + 7) / 8 * 8 + 8;
 			bnd_words += 6 * (size_t)T.bnd_len;
 			park_words += (size_t)n_strips * 32 * (2 * R + 3);
 			for (int h = 0; h < (q.b >= 0 ? 2 : 1); ++h) {
@@ -1047,7 +1049,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 	}
 	int32_t n_redo = 0;
 	SSW_CUDA_OK(cudaMemcpyAsync(&n_redo, gb + o_cnt, 4, cudaMemcpyDeviceToHost, e->stream));
-	SSW_CUDA_OK(cudaMemcpyAsync(results, e->d_out.p, sizeof(ssw_batch_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost, e->stream));
+	if (e->staged.copy(results, e->d_out.p, sizeof(ssw_batch_result) * (size_t)n_pairs, e->stream)) return -1;
 	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
 	if (n_redo > redo_cap) {                     /* more overflows than the list holds: find them by scanning is not possible -> general path */
 		return 0;

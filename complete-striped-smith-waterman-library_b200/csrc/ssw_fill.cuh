@@ -45,7 +45,7 @@
 #define SSW_STRIP_R 10                      /* rows per lane of the strip kernel: 320 rows per strip (config 5: R=10 247 ms, 16: 268, 20: 257, 8: 365) */
 #endif
 #define SSW_STRIP_MAXW 16                   /* warps per CTA of the strip kernel */
-#define SSW_STRIP_LAG 40                    /* a strip's last lane ends a super-block this many columns before the strip above */
+#define SSW_STRIP_LAG 48                    /* a strip's last lane ends a super-block this many columns before the strip above */
 #define SSW_STRIP_SUPER 4096                /* columns per super-block (granularity of early termination) */
 #define SSW_STRIP_BPAD 32                   /* words in front of every boundary array (scan positions down to -32) */
 
@@ -429,7 +429,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
  * run as a pipeline: for every column strip s takes the bottom row of strip s-1 (H, F, partial column maximum)
  * from that strip's boundary arrays and publishes its own.  prog[s] (shared memory) is the number of columns
  * strip s has published.  Strip s's last lane ends a super-block SSW_STRIP_LAG*s columns before the block's
- * end, so everything it needs from strip s-1 (36 columns ahead of its last lane) has been published; between
+ * end, so everything it needs from strip s-1 (40 columns ahead of its last lane) has been published; between
  * super-blocks a strip's lane registers are parked in global memory.  Tasks depend only on lexicographically
  * smaller (super-block, strip) tasks and every warp runs its tasks in that order, so the spin-waits cannot
  * dead-lock.  The reverse pass raises a CTA-wide stop flag when the last strip meets the terminate score;
@@ -517,11 +517,11 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 
 	const uint8_t* rp = reinterpret_cast<const uint8_t*>(refs) + T.ref_off;
 	const uint32_t negO = pack2(-gapO, -gapO), negE = pack2(-gapE, -gapE);
-	const int col_hi = T.ref_len + SSW_REF_PAD - 4, col_lo = -SSW_REF_PAD + 3;
+	const int col_hi = T.ref_len + SSW_REF_PAD - 8, col_lo = -SSW_REF_PAD + 7;
 	const ssw_saddr pbase = ssw_sadd(ssw_sbase(prof), lane * 4);
 	const ssw_saddr ptail = ssw_sadd(ssw_sbase(prof), A4 * 128 + lane * REM);
 	const int start = -32;                               /* first last-lane position: lane 0 starts at -1 */
-	const int end = (T.p1 + 3) & ~3;                     /* last-lane positions run over [start, end) */
+	const int end = (T.p1 + 7) & ~7;                     /* last-lane positions run over [start, end) */
 
 	for (int sb = 0; sb < T.n_super; ++sb) {
 		for (int s = s_first + warp; s < s_last; s += NW) {
@@ -573,12 +573,16 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 				cH = ssw_ldcg(bin + sL + 31); cF = ssw_ldcg(bin + T.bnd_len + sL + 31); cC = ssw_ldcg(bin + 2 * T.bnd_len + sL + 31);
 			}
 
-			for (; sL < hi; sL += 4) {
-				uint4 gH = make_uint4(0, 0, 0, 0), gF = gH, gC = gH;
+			/* one loop body = 8 scan positions in two halves of 4: the wait for the producer, the stop-flag poll, the
+			 * progress word and the cursor updates are paid once per body, the boundary groups (4 words per array) are
+			 * loaded and stored per half */
+			for (; sL < hi; sL += 8) {
+				uint4 gH[2], gF[2], gC[2];
+				gH[0] = gH[1] = gF[0] = gF[1] = gC[0] = gC[1] = make_uint4(0, 0, 0, 0);
 				int st = 0;                                  /* the stop flag as lane 0 saw it (warp-uniform after the broadcast) */
 				if (lane == 0) {
 					if (s > 0) {
-						const int need = min(sL + 36, end);
+						const int need = min(sL + 40, end);
 						if (SPLIT && s == s_first) {
 							/* producer is another CTA: its progress word is read one loop body ahead of the need (the load
 							 * of the previous body has landed by now), so the wait loop is only entered when this strip has
@@ -590,64 +594,76 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 							while (prog[s - 1] < need && !(st = *stop)) { SSW_SPIN_PAUSE(); }
 							__threadfence_block();
 						}
-						gH = ssw_ldcg(reinterpret_cast<const uint4*>(bin + sL + 32));
-						gF = ssw_ldcg(reinterpret_cast<const uint4*>(bin + T.bnd_len + sL + 32));
-						gC = ssw_ldcg(reinterpret_cast<const uint4*>(bin + 2 * T.bnd_len + sL + 32));
+#pragma unroll
+						for (int h = 0; h < 2; ++h) {
+							gH[h] = ssw_ldcg(reinterpret_cast<const uint4*>(bin + sL + 32 + 4 * h));
+							gF[h] = ssw_ldcg(reinterpret_cast<const uint4*>(bin + T.bnd_len + sL + 32 + 4 * h));
+							gC[h] = ssw_ldcg(reinterpret_cast<const uint4*>(bin + 2 * T.bnd_len + sL + 32 + 4 * h));
+						}
 					}
 					if (TERM) st = *stop;
 				}
 				st = __shfl_sync(FULL, st, 0);
 				if (TERM) { if (st) { stopped = true; break; } }
-				const uint32_t bHv[4] = {cH, gH.x, gH.y, gH.z}, bFv[4] = {cF, gF.x, gF.y, gF.z}, bCv[4] = {cC, gC.x, gC.y, gC.z};
-				cH = gH.w; cF = gF.w; cC = gC.w;
-				uint32_t cmv[4], hv[4], fv[4];
-				const bool maybe_counted = sp0 + 3 >= 0 && sp0 < T.p1;
+				const bool maybe_counted = sp0 + 7 >= 0 && sp0 < T.p1;
+				int hit = 0;
 #pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					/* lane 0 takes the boundary words (zero in the other lanes) instead of the shuffled ones: a multiply-add
-					 * by 0/1 on the FMA pipe rather than a select on the ALU pipe, which is the busy one */
-					const uint32_t inH = __shfl_up_sync(FULL, outH, 1) * top_keep + bHv[j];
-					const uint32_t inF = __shfl_up_sync(FULL, outF, 1) * top_keep + bFv[j];
-					const uint32_t inC = __shfl_up_sync(FULL, outC, 1) * top_keep + bCv[j];
-					int letter = (int)lptr[DIR * j];
-					if (DIR < 0) { if (sp0 + j < 0) letter = n; }   /* right of cend; forward scans start inside the null pad */
-					uint32_t sc[R], Hn[R];
-					ssw_load_scores<R>(sc, pbase, ptail, letter);
-					uint32_t own;
-					ssw_cells<R>(Hd, E, sc, Hn, inH, inF, inC, negO, negE, outH, outF, outC, own);
-					cmv[j] = outC; hv[j] = outH; fv[j] = outF;
-					const uint32_t nb = __vmaxs2(lb.best, own);
-					if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, 0, T.p1);
-				}
-				/* the last lane publishes the strip's bottom row (the last strip: the column maxima) */
-				if (lane == 31 && sL >= 0) {
-					if (s + 1 < T.n_strips) {
-						*reinterpret_cast<uint4*>(bout + sL) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-						*reinterpret_cast<uint4*>(bout + T.bnd_len + sL) = make_uint4(fv[0], fv[1], fv[2], fv[3]);
-						*reinterpret_cast<uint4*>(bout + 2 * T.bnd_len + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
-						if (SPLIT && s + 1 == s_last) {
-							/* consumer in another CTA: device-scope release, amortised over 128 columns (and the final ones) */
-							if (((sL + 4) & 127) == 0 || sL + 4 >= hi) ssw_st_release(gprog_out, sL + 4);
-						} else {
-							__threadfence_block();
-							prog[s] = sL + 4;
+				for (int h = 0; h < 2; ++h) {
+					const uint32_t bHv[4] = {cH, gH[h].x, gH[h].y, gH[h].z}, bFv[4] = {cF, gF[h].x, gF[h].y, gF[h].z}, bCv[4] = {cC, gC[h].x, gC[h].y, gC[h].z};
+					cH = gH[h].w; cF = gF[h].w; cC = gC[h].w;
+					uint32_t cmv[4], hv[4], fv[4];
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						/* lane 0 takes the boundary words (zero in the other lanes) instead of the shuffled ones: a multiply-add
+						 * by 0/1 on the FMA pipe rather than a select on the ALU pipe, which is the busy one */
+						const uint32_t inH = __shfl_up_sync(FULL, outH, 1) * top_keep + bHv[j];
+						const uint32_t inF = __shfl_up_sync(FULL, outF, 1) * top_keep + bFv[j];
+						const uint32_t inC = __shfl_up_sync(FULL, outC, 1) * top_keep + bCv[j];
+						int letter = (int)lptr[DIR * (4 * h + j)];
+						if (DIR < 0) { if (sp0 + 4 * h + j < 0) letter = n; }   /* right of cend; forward scans start inside the null pad */
+						uint32_t sc[R], Hn[R];
+						ssw_load_scores<R>(sc, pbase, ptail, letter);
+						uint32_t own;
+						ssw_cells<R>(Hd, E, sc, Hn, inH, inF, inC, negO, negE, outH, outF, outC, own);
+						cmv[j] = outC; hv[j] = outH; fv[j] = outF;
+						const uint32_t nb = __vmaxs2(lb.best, own);
+						if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + 4 * h + j, 0, T.p1);
+					}
+					/* the last lane stores the strip's bottom row (the last strip: the column maxima) */
+					const int g = sL + 4 * h;
+					if (lane == 31 && g >= 0) {
+						if (s + 1 < T.n_strips) {
+							*reinterpret_cast<uint4*>(bout + g) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+							*reinterpret_cast<uint4*>(bout + T.bnd_len + g) = make_uint4(fv[0], fv[1], fv[2], fv[3]);
+							*reinterpret_cast<uint4*>(bout + 2 * T.bnd_len + g) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
+						} else if (T.cm_off >= 0 && g < T.p1) {
+							*reinterpret_cast<uint4*>(colmax + T.cm_off + g) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
 						}
-					} else if (T.cm_off >= 0 && sL < T.p1) {
-						*reinterpret_cast<uint4*>(colmax + T.cm_off + sL) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
+					}
+					if (TERM && s + 1 == T.n_strips) {
+						if (lane == 31 && T.term_a >= 0) {
+#pragma unroll
+							for (int j = 0; j < 4; ++j)
+								if (g + j >= 0 && g + j < T.p1 && half_of(cmv[j], 0) == T.term_a) hit = 1;
+						}
+					}
+				}
+				/* publish: everything up to scan position sL + 8 of this strip's bottom row is in memory */
+				if (lane == 31 && sL + 4 >= 0 && s + 1 < T.n_strips) {
+					if (SPLIT && s + 1 == s_last) {
+						/* consumer in another CTA: device-scope release, amortised over 128 columns (and the final ones) */
+						if (((sL + 8) & 127) == 0 || sL + 8 >= hi) ssw_st_release(gprog_out, sL + 8);
+					} else {
+						__threadfence_block();
+						prog[s] = sL + 8;
 					}
 				}
 				if (TERM && s + 1 == T.n_strips) {
-					int hit = 0;
-					if (lane == 31 && T.term_a >= 0) {
-#pragma unroll
-						for (int j = 0; j < 4; ++j)
-							if (sL + j >= 0 && sL + j < T.p1 && half_of(cmv[j], 0) == T.term_a) hit = 1;
-					}
 					if (__any_sync(FULL, hit)) { if (lane == 0) *stop = 1; stopped = true; break; }
 				}
-				sp0 += 4;
+				sp0 += 8;
 				{
-					const int ncol = DIR > 0 ? min(col + 4, col_hi) : max(col - 4, col_lo);
+					const int ncol = DIR > 0 ? min(col + 8, col_hi) : max(col - 8, col_lo);
 					lptr += ncol - col;
 					col = ncol;
 				}

@@ -2,6 +2,7 @@
 #ifndef SSW_HOST_H
 #define SSW_HOST_H
 
+#include <string.h>
 #include "ssw_common.cuh"
 
 /* counts device allocations and frees made through SswDevBuf: the engine re-reads the free device memory only when
@@ -46,6 +47,44 @@ inline size_t ssw_free_device_bytes()
 	}
 	return cache[dev];
 }
+
+/* Large device -> pageable-host copies: a plain cudaMemcpy into pageable memory runs at a few GB/s (the driver stages
+ * it through one small pinned buffer).  This stages through two pinned 8 MB buffers: the copy of chunk k+1 runs while the
+ * host moves chunk k to its destination. */
+struct SswStagedD2H {
+	void* pin[2] = {nullptr, nullptr};
+	cudaEvent_t ev[2] = {nullptr, nullptr};
+	static constexpr size_t CHUNK = (size_t)8 << 20;
+	int copy(void* dst, const void* src_dev, size_t bytes, cudaStream_t st)
+	{
+		if (bytes < 2 * CHUNK) {
+			if (cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+			return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
+		}
+		for (int i = 0; i < 2; ++i)
+			if (!pin[i]) {
+				if (cudaMallocHost(&pin[i], CHUNK) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+			}
+		const size_t n = (bytes + CHUNK - 1) / CHUNK;
+		for (size_t k = 0; k <= n; ++k) {
+			if (k < n) {
+				const size_t len = k + 1 < n ? CHUNK : bytes - k * CHUNK;
+				if (cudaMemcpyAsync(pin[k & 1], (const char*)src_dev + k * CHUNK, len, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+				cudaEventRecord(ev[k & 1], st);
+			}
+			if (k > 0) {
+				const size_t j = k - 1, len = j + 1 < n ? CHUNK : bytes - j * CHUNK;
+				if (cudaEventSynchronize(ev[j & 1]) != cudaSuccess) return -1;
+				memcpy((char*)dst + j * CHUNK, pin[j & 1], len);
+			}
+		}
+		return 0;
+	}
+	void release()
+	{
+		for (int i = 0; i < 2; ++i) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); pin[i] = nullptr; ev[i] = nullptr; }
+	}
+};
 
 /* CUDA-event stopwatch on one stream */
 struct SswTimer {
