@@ -4,7 +4,8 @@
  *
  * The reference driver re-opens and re-parses the target file for every read and issues one blocking
  * ssw_align per (read, reference) pair (main.c:462-532, :493-494).  This driver parses both files once,
- * puts every pair -- and, with -r, every reverse-complement pair -- into ONE ssw_align_batch call, and
+ * puts every pair -- and, with -r, every reverse-complement pair -- into ONE ssw_align_batch_text call (letters are
+ * translated and reverse-complemented on the device), and
  * then prints the records in the reference's order and format (BLAST-like, main.c:129-206, or SAM,
  * main.c:207-244).  Same options: -m -x -o -e -p -a FILE -c -f N -r -s -h.
  *
@@ -266,18 +267,14 @@ int main(int argc, char** argv)
 		sam = false;
 	}
 
-	/* encode everything once: queries = reads (then their reverse complements), references */
+	/* one batch: the letters go to the device as they are; translation with `table`, the reverse complements (query
+	 * n + k = reverse complement of read k) and the padded reference layout are made there */
 	const bool rc = reverse && !protein;
-	std::vector<std::string> rc_seq(rc ? reads.size() : 0);
-	std::vector<int8_t> qcodes, rcodes;
+	std::vector<std::string> rc_seq(rc ? reads.size() : 0);          /* only for printing the minus-strand records */
+	std::string qtext, rtext;
 	std::vector<int64_t> qoff(1, 0), roff(1, 0);
-	for (const Record& r : reads) { for (char c : r.seq) qcodes.push_back(table[(int)(c & 127)]); qoff.push_back((int64_t)qcodes.size()); }
-	if (rc) for (size_t i = 0; i < reads.size(); ++i) {
-		rc_seq[i] = revcomp(reads[i].seq);
-		for (char c : rc_seq[i]) qcodes.push_back(table[(int)(c & 127)]);
-		qoff.push_back((int64_t)qcodes.size());
-	}
-	for (const Record& r : refs) { for (char c : r.seq) rcodes.push_back(table[(int)(c & 127)]); roff.push_back((int64_t)rcodes.size()); }
+	for (const Record& r : reads) { qtext += r.seq; qoff.push_back((int64_t)qtext.size()); }
+	for (const Record& r : refs) { rtext += r.seq; roff.push_back((int64_t)rtext.size()); }
 	const int32_t n_q = (int32_t)reads.size() * (rc ? 2 : 1), n_r = (int32_t)refs.size();
 	if (n_q == 0 || n_r == 0) return 0;
 
@@ -288,29 +285,32 @@ int main(int argc, char** argv)
 	P.mat = mat.data(); P.n = n; P.gap_open = (uint8_t)gap_open; P.gap_extend = (uint8_t)gap_ext;
 	P.flag = path ? 2 : 0; P.filters = (uint16_t)filter; P.filterd = 0; P.mask_len = -1; P.score_size = 2;
 	std::vector<s_align*> out((size_t)n_q * n_r, nullptr);
-	if (ssw_align_batch(eng, &P, n_q, qcodes.data(), qoff.data(), n_r, rcodes.data(), roff.data(), (int64_t)n_q * n_r, nullptr, nullptr, out.data())) {
-		fprintf(stderr, "ssw_align_batch failed\n");
+	if (ssw_align_batch_text(eng, &P, table, rc ? 1 : 0, (int32_t)reads.size(), qtext.data(), qoff.data(), n_r, rtext.data(), roff.data(),
+	                         (int64_t)n_q * n_r, nullptr, nullptr, out.data())) {
+		fprintf(stderr, "ssw_align_batch_text failed\n");
 		return 1;
 	}
+	/* host-side codes are only needed by the SAM writer (mark_mismatch): translated on first use */
+	std::vector<std::vector<int8_t>> ref_codes(refs.size());
+	auto codes_of = [&](const std::string& text) { std::vector<int8_t> c(text.size()); for (size_t i = 0; i < text.size(); ++i) c[i] = table[(int)(text[i] & 127)]; return c; };
+	auto ref_num_of = [&](int32_t ri) -> const int8_t* { if (ref_codes[ri].empty()) ref_codes[ri] = codes_of(refs[ri].seq); return ref_codes[ri].data(); };
 
 	for (size_t qi = 0; qi < reads.size(); ++qi) {
 		for (int32_t ri = 0; ri < n_r; ++ri) {
 			s_align* res = out[qi * n_r + ri];
 			s_align* res_rc = rc ? out[(reads.size() + qi) * n_r + ri] : nullptr;
-			const int8_t* ref_num = rcodes.data() + roff[ri];
 			if (!res) {
 				fprintf(stderr, "Warning: Alignment between the following sequences is failed.\nref_name: %s\nread_name: %s\n\n", refs[ri].name.c_str(), reads[qi].name.c_str());
 				continue;
 			}
 			if (res_rc && res_rc->score1 > res->score1 && res_rc->score1 >= filter) {
 				if (res_rc->flag == 2) fprintf(stderr, "Warning: The reverse compliment alignment of the following sequences may miss a small part.\nref_seq: %s\nread_seq: %s\n\n", refs[ri].name.c_str(), reads[qi].name.c_str());
-				const int8_t* qn = qcodes.data() + qoff[reads.size() + qi];
-				if (sam) write_sam(res_rc, refs[ri], reads[qi], rc_seq[qi], ref_num, qn, true);
+				if (rc_seq[qi].empty()) rc_seq[qi] = revcomp(reads[qi].seq);
+				if (sam) { const std::vector<int8_t> qn = codes_of(rc_seq[qi]); write_sam(res_rc, refs[ri], reads[qi], rc_seq[qi], ref_num_of(ri), qn.data(), true); }
 				else write_blast(res_rc, refs[ri], reads[qi], rc_seq[qi], table, true);
 			} else if (res->score1 > 0 && res->score1 >= filter) {
 				if (res->flag == 2) fprintf(stderr, "Warning: The alignment of the following sequences may miss a small part.\nref_seq: %s\nread_seq: %s\n\n", refs[ri].name.c_str(), reads[qi].name.c_str());
-				const int8_t* qn = qcodes.data() + qoff[qi];
-				if (sam) write_sam(res, refs[ri], reads[qi], reads[qi].seq, ref_num, qn, false);
+				if (sam) { const std::vector<int8_t> qn = codes_of(reads[qi].seq); write_sam(res, refs[ri], reads[qi], reads[qi].seq, ref_num_of(ri), qn.data(), false); }
 				else write_blast(res, refs[ri], reads[qi], reads[qi].seq, table, false);
 			} else if (res->score1 <= 0) {
 				fprintf(stderr, "There is no identical residue between the following reference and read seqeunces.\nref_name: %s\nread_name: %s\n\n", refs[ri].name.c_str(), reads[qi].name.c_str());

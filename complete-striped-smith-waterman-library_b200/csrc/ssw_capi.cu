@@ -102,25 +102,12 @@ extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t 
 	return record_from(r, pool.data());
 }
 
-extern "C" int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
-                               int32_t n_queries, const int8_t* queries, const int64_t* query_off,
-                               int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
-                               int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
-                               s_align** out)
+namespace {
+/* align the resident sequences and turn the records into heap s_align objects */
+int collect_batch(ssw_engine* e, const ssw_batch_params* params, int32_t n_queries, const int64_t* query_off,
+                  int32_t n_refs, const int64_t* ref_off, int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out)
 {
-	if (!params || !out) return -1;
-	std::unique_lock<std::mutex> lock(g_mu, std::defer_lock);
-	if (!e) {                                   /* NULL: the process-wide engine that also serves ssw_align */
-		lock.lock();
-		e = default_engine();
-		if (!e) return -1;
-	}
-	if (params->mask_len >= 0 && params->mask_len < 15)
-		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
-	int rc = ssw_engine_set_sequences(e, n_queries, queries, query_off, n_refs, refs, ref_off);
-	if (rc) return rc;
 	std::vector<ssw_batch_result> res((size_t)n_pairs);
-	/* CIGAR pool: a path has at most readLen + refLen + 2 words */
 	int64_t cap = 0;
 	if (params->flag & 7) {
 		for (int64_t p = 0; p < n_pairs; ++p) {
@@ -136,10 +123,55 @@ extern "C" int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
 	}
 	std::vector<uint32_t> pool((size_t)cap + 8);
 	int64_t used = 0;
-	rc = ssw_engine_align(e, params, n_pairs, pair_query, pair_ref, res.data(), pool.data(), (int64_t)pool.size(), &used);
+	const int rc = ssw_engine_align(e, params, n_pairs, pair_query, pair_ref, res.data(), pool.data(), (int64_t)pool.size(), &used);
 	if (rc) return rc;
 	for (int64_t p = 0; p < n_pairs; ++p) out[p] = record_from(res[p], pool.data());
 	return 0;
+}
+}  // namespace
+
+extern "C" int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
+                               int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                               int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
+                               int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                               s_align** out)
+{
+	if (!params || !out) return -1;
+	std::unique_lock<std::mutex> lock(g_mu, std::defer_lock);
+	if (!e) {                                   /* NULL: the process-wide engine that also serves ssw_align */
+		lock.lock();
+		e = default_engine();
+		if (!e) return -1;
+	}
+	if (params->mask_len >= 0 && params->mask_len < 15)
+		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+	const int rc = ssw_engine_set_sequences(e, n_queries, queries, query_off, n_refs, refs, ref_off);
+	if (rc) return rc;
+	return collect_batch(e, params, n_queries, query_off, n_refs, ref_off, n_pairs, pair_query, pair_ref, out);
+}
+
+extern "C" int ssw_align_batch_text(ssw_engine* e, const ssw_batch_params* params, const int8_t* table, int32_t add_reverse_complement,
+                                    int32_t n_queries, const char* queries, const int64_t* query_off,
+                                    int32_t n_refs, const char* refs, const int64_t* ref_off,
+                                    int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                                    s_align** out)
+{
+	if (!params || !out || !table) return -1;
+	std::unique_lock<std::mutex> lock(g_mu, std::defer_lock);
+	if (!e) {
+		lock.lock();
+		e = default_engine();
+		if (!e) return -1;
+	}
+	if (params->mask_len >= 0 && params->mask_len < 15)
+		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+	const int rc = ssw_engine_set_sequences_text(e, n_queries, queries, query_off, n_refs, refs, ref_off, table, params->n, add_reverse_complement);
+	if (rc) return rc;
+	/* query k + n_queries is the reverse complement of query k */
+	const int32_t nq = n_queries * (add_reverse_complement ? 2 : 1);
+	std::vector<int64_t> qoff(query_off, query_off + n_queries + 1);
+	if (add_reverse_complement) for (int i = 1; i <= n_queries; ++i) qoff.push_back(query_off[n_queries] + query_off[i]);
+	return collect_batch(e, params, nq, qoff.data(), n_refs, ref_off, n_pairs, pair_query, pair_ref, out);
 }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -26,6 +26,7 @@
 #include "ssw_traceback.cuh"
 #include "ssw_emul.cuh"
 #include "ssw_grid.cuh"
+#include "ssw_text.cuh"
 #include "../../include/ssw_batch.h"
 
 #include <chrono>
@@ -87,6 +88,7 @@ struct ssw_engine {
 	std::vector<int8_t> h_q, h_r;    /* host copies (codes), used to re-pad when the alphabet size changes */
 	std::vector<int64_t> h_r_off;
 	int padded_n = -1;               /* null letter currently stored in the reference pads */
+	bool from_text = false;          /* sequences were translated on the device: no host copy to re-pad from */
 	SswDevBuf d_q, d_r, d_mat;
 
 	/* scratch */
@@ -281,6 +283,10 @@ extern "C" int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t)
 int ssw_engine::upload_refs(int n)
 {
 	if (padded_n == n && d_r.p) return 0;
+	if (from_text) {
+		fprintf(stderr, "[libssw-b200] sequences were set as text for an alphabet of %d letters; this call uses %d\n", padded_n, n);
+		return -1;
+	}
 	int64_t total = 0;
 	r_off.resize(n_r);
 	for (int i = 0; i < n_r; ++i) {
@@ -307,6 +313,7 @@ extern "C" int ssw_engine_set_sequences(ssw_engine* e,
 	if (!e || n_queries < 0 || n_refs < 0 || (n_queries && (!queries || !query_off)) || (n_refs && (!refs || !ref_off))) return -1;
 	SSW_CUDA_OK(cudaSetDevice(e->device));
 	e->n_q = n_queries; e->n_r = n_refs;
+	e->from_text = false;
 	e->q_off.assign(query_off, query_off + n_queries + 1);
 	e->h_q.assign(queries, queries + query_off[n_queries]);
 	e->h_r_off.assign(ref_off, ref_off + n_refs + 1);
@@ -317,6 +324,66 @@ extern "C" int ssw_engine_set_sequences(ssw_engine* e,
 	SSW_CUDA_OK(cudaMemcpyAsync(e->d_q.p, e->h_q.data(), e->h_q.size(), cudaMemcpyHostToDevice, e->stream));
 	e->padded_n = -1;           /* the null letter depends on the alphabet size given at align time */
 	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+extern "C" int ssw_engine_set_sequences_text(ssw_engine* e,
+                                             int32_t n_queries, const char* queries, const int64_t* query_off,
+                                             int32_t n_refs, const char* refs, const int64_t* ref_off,
+                                             const int8_t* table, int32_t n, int32_t add_reverse_complement)
+{
+	if (!e || !table || n < 1 || n > 64 || n_queries < 0 || n_refs < 0 || (n_queries && (!queries || !query_off)) ||
+	    (n_refs && (!refs || !ref_off)))
+		return -1;
+	SSW_CUDA_OK(cudaSetDevice(e->device));
+	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
+	const int rc = add_reverse_complement ? 1 : 0;
+	e->n_q = n_queries * (1 + rc); e->n_r = n_refs;
+	e->q_off.assign(query_off, query_off + n_queries + 1);
+	if (rc) for (int i = 1; i <= n_queries; ++i) e->q_off.push_back(qb + query_off[i]);
+	e->h_q.clear(); e->h_r.clear(); e->h_r_off.clear();
+	e->r_len.resize(n_refs);
+	e->r_off.resize(n_refs);
+	int64_t total = 0;
+	for (int i = 0; i < n_refs; ++i) {
+		e->r_len[i] = (int32_t)(ref_off[i + 1] - ref_off[i]);
+		total += SSW_REF_PAD;
+		e->r_off[i] = total;
+		total += e->r_len[i];
+		total += SSW_REF_PAD;
+		total = (total + 15) / 16 * 16;
+	}
+	total += 2 * SSW_REF_PAD;
+	/* staging: texts, offsets, destination offsets, table */
+	const size_t o_qt = 0, o_rt = (size_t)(qb + 255) / 256 * 256, o_qo = o_rt + (size_t)(rb + 255) / 256 * 256;
+	const size_t o_ro = o_qo + 8 * (size_t)(n_queries + 1), o_rd = o_ro + 8 * (size_t)(n_refs + 1), o_tab = o_rd + 8 * (size_t)(n_refs + 1);
+	if (e->d_grid.ensure(o_tab + 128 + 256)) return -1;
+	if (e->d_q.ensure((size_t)qb * (size_t)(1 + rc) + 16)) return -1;
+	if (e->d_r.ensure((size_t)total)) return -1;
+	uint8_t* st = e->d_grid.as<uint8_t>();
+	if (qb) SSW_CUDA_OK(cudaMemcpyAsync(st + o_qt, queries, (size_t)qb, cudaMemcpyHostToDevice, e->stream));
+	if (rb) SSW_CUDA_OK(cudaMemcpyAsync(st + o_rt, refs, (size_t)rb, cudaMemcpyHostToDevice, e->stream));
+	if (n_queries) SSW_CUDA_OK(cudaMemcpyAsync(st + o_qo, query_off, 8 * (size_t)(n_queries + 1), cudaMemcpyHostToDevice, e->stream));
+	if (n_refs) {
+		SSW_CUDA_OK(cudaMemcpyAsync(st + o_ro, ref_off, 8 * (size_t)(n_refs + 1), cudaMemcpyHostToDevice, e->stream));
+		SSW_CUDA_OK(cudaMemcpyAsync(st + o_rd, e->r_off.data(), 8 * (size_t)n_refs, cudaMemcpyHostToDevice, e->stream));
+	}
+	SSW_CUDA_OK(cudaMemcpyAsync(st + o_tab, table, 128, cudaMemcpyHostToDevice, e->stream));
+	SSW_CUDA_OK(cudaMemsetAsync(e->d_r.p, n, (size_t)total, e->stream));          /* null letters everywhere, codes on top */
+	SswTextArgs A;
+	A.q_bytes = qb; A.r_bytes = rb; A.n_q = n_queries; A.n_r = n_refs; A.add_rc = rc; A.pad_ = 0;
+	const int64_t work = std::max<int64_t>(qb, rb);
+	if (work > 0) {
+		const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, (int64_t)e->sm_count * 16);
+		ssw_launch(ssw_translate_kernel, dim3(blocks), dim3(256), 0, e->stream, A, (const uint8_t*)(st + o_qt),
+		           (const int64_t*)reinterpret_cast<int64_t*>(st + o_qo), (const uint8_t*)(st + o_rt),
+		           (const int64_t*)reinterpret_cast<int64_t*>(st + o_ro), (const int64_t*)reinterpret_cast<int64_t*>(st + o_rd),
+		           (const int8_t*)reinterpret_cast<int8_t*>(st + o_tab), e->d_q.as<int8_t>(), e->d_r.as<int8_t>());
+		SSW_CUDA_OK(cudaGetLastError());
+	}
+	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	e->padded_n = n;
+	e->from_text = true;
 	return 0;
 }
 

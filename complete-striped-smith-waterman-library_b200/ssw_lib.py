@@ -160,6 +160,30 @@ class BatchAligner(object):
         self.n_q, self.n_r = len(queries), len(refs)
         self._lens = (np.diff(qo), np.diff(ro))
 
+    def set_sequences_text(self, queries, refs, table, n, add_reverse_complement=False):
+        """Sequences as text (bytes / str): translated to codes with `table` (128 int8 entries) on the device; with
+        add_reverse_complement the reverse complement of query k becomes query len(queries) + k."""
+        qs = [q.encode() if isinstance(q, str) else bytes(q) for q in queries]
+        rs = [r.encode() if isinstance(r, str) else bytes(r) for r in refs]
+        qt, rt = b"".join(qs), b"".join(rs)
+        qo = np.zeros(len(qs) + 1, dtype=np.int64); qo[1:] = np.cumsum([len(q) for q in qs])
+        ro = np.zeros(len(rs) + 1, dtype=np.int64); ro[1:] = np.cumsum([len(r) for r in rs])
+        tab = np.ascontiguousarray(table, dtype=np.int8)
+        assert tab.size == 128
+        f = self.lib.ssw_engine_set_sequences_text
+        f.argtypes = [ct.c_void_p, ct.c_int32, ct.c_char_p, ct.POINTER(ct.c_int64), ct.c_int32, ct.c_char_p, ct.POINTER(ct.c_int64),
+                      ct.POINTER(ct.c_int8), ct.c_int32, ct.c_int32]
+        f.restype = ct.c_int
+        rv = f(self.h, len(qs), qt, qo.ctypes.data_as(ct.POINTER(ct.c_int64)), len(rs), rt, ro.ctypes.data_as(ct.POINTER(ct.c_int64)),
+               tab.ctypes.data_as(ct.POINTER(ct.c_int8)), int(n), 1 if add_reverse_complement else 0)
+        if rv:
+            raise RuntimeError("ssw_engine_set_sequences_text failed (%d)" % rv)
+        ql = np.diff(qo)
+        if add_reverse_complement:
+            ql = np.concatenate([ql, ql])
+        self.n_q, self.n_r = len(ql), len(rs)
+        self._lens = (ql, np.diff(ro))
+
     def align(self, mat, n, gap_open=3, gap_extend=1, flag=0, filters=0, filterd=0, mask_len=-1, score_size=2,
               pair_query=None, pair_ref=None, want_cigar=None):
         """Align pairs of the resident sequences; returns (results[RESULT_DTYPE], cigar_pool[uint32])."""

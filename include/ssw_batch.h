@@ -67,6 +67,17 @@ int ssw_engine_set_sequences(ssw_engine* e,
                              int32_t n_refs, const int8_t* refs, const int64_t* ref_off);
 
 /*
+ * The same for sequences given as TEXT: the letters are translated to codes on the device with `table` (128 entries,
+ * the reference CLI's nt_table / aa_table, main.c:72-93; bytes are masked to 7 bits), for an alphabet of n codes
+ * (the n of the later align calls).  add_reverse_complement != 0 also makes every query's reverse complement resident,
+ * as query number n_queries + k (complement on the letters as main.c:95-116 does it: A<->T, C<->G, N->N, other -> 4).
+ */
+int ssw_engine_set_sequences_text(ssw_engine* e,
+                                  int32_t n_queries, const char* queries, const int64_t* query_off,
+                                  int32_t n_refs, const char* refs, const int64_t* ref_off,
+                                  const int8_t* table, int32_t n, int32_t add_reverse_complement);
+
+/*
  * Align pairs of resident sequences.
  *   pair_query / pair_ref   n_pairs indices; both NULL: the full grid, pair p = query p / n_refs x ref p % n_refs
  *   results                 n_pairs records (host memory)
@@ -88,6 +99,14 @@ int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
                     int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
                     int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
                     s_align** out);
+
+/* ssw_align_batch for text sequences (ssw_engine_set_sequences_text + align + s_align records); with
+ * add_reverse_complement the queries n_queries .. 2*n_queries-1 are the reverse complements. */
+int ssw_align_batch_text(ssw_engine* e, const ssw_batch_params* params, const int8_t* table, int32_t add_reverse_complement,
+                         int32_t n_queries, const char* queries, const int64_t* query_off,
+                         int32_t n_refs, const char* refs, const int64_t* ref_off,
+                         int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                         s_align** out);
 
 /* Device-time breakdown of the last ssw_engine_align call (CUDA events on the engine's stream), in ms. */
 typedef struct {

@@ -33,6 +33,43 @@ int ssw_align_batch(ssw_engine* e, const ssw_batch_params* P,
 	return 0;
 }
 
+/* text variant: translate (and reverse-complement) on the host, then as above */
+static int rc_letter(int c)
+{
+	switch (c) {
+	case 'A': case 'a': return 'T';
+	case 'C': case 'c': return 'G';
+	case 'G': case 'g': return 'C';
+	case 'T': case 't': case 'U': case 'u': return 'A';
+	case 'N': case 'n': return 'N';
+	default: return 4;
+	}
+}
+
+int ssw_align_batch_text(ssw_engine* e, const ssw_batch_params* P, const int8_t* table, int32_t add_rc,
+                         int32_t n_queries, const char* queries, const int64_t* query_off,
+                         int32_t n_refs, const char* refs, const int64_t* ref_off,
+                         int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out)
+{
+	const int64_t qb = query_off[n_queries], rb = ref_off[n_refs];
+	const int32_t nq = n_queries * (add_rc ? 2 : 1);
+	int8_t* qc = (int8_t*)malloc((size_t)(qb * (add_rc ? 2 : 1)) + 1);
+	int8_t* rcodes = (int8_t*)malloc((size_t)rb + 1);
+	int64_t* qo = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nq + 1));
+	for (int64_t i = 0; i < qb; ++i) qc[i] = table[queries[i] & 127];
+	for (int64_t i = 0; i < rb; ++i) rcodes[i] = table[refs[i] & 127];
+	for (int32_t k = 0; k <= n_queries; ++k) qo[k] = query_off[k];
+	if (add_rc)
+		for (int32_t k = 0; k < n_queries; ++k) {
+			const int64_t b = query_off[k], len = query_off[k + 1] - b;
+			for (int64_t p = 0; p < len; ++p) qc[qb + b + p] = table[rc_letter(queries[b + len - 1 - p]) & 127];
+			qo[n_queries + k + 1] = qb + query_off[k + 1];
+		}
+	const int rc = ssw_align_batch(e, P, nq, qc, qo, n_refs, rcodes, ref_off, n_pairs, pair_query, pair_ref, out);
+	free(qc); free(rcodes); free(qo);
+	return rc;
+}
+
 void align_destroy(s_align* a) { oracle_align_destroy((oracle_align_t*)a); }
 
 int32_t mark_mismatch(int32_t ref_begin1, int32_t read_begin1, int32_t read_end1, const int8_t* ref, const int8_t* read,

@@ -228,3 +228,52 @@ def test_emulated_wide_bands_multi_tile(oracle, capfd):
             assert len(got["cigar"]) >= 1
     eng.set_option("tb_maxbw", -1)
     eng.close()
+
+
+def test_emulated_text_sequences(oracle, capfd):
+    """ssw_engine_set_sequences_text: letter -> code translation, reverse complements and the padded reference layout
+    made on the device give the same records as host-translated codes (incl. N, lower case and other letters)."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    rng = np.random.default_rng(4242)
+    letters = np.frombuffer(b"ACGTacgtNnUuRY-", dtype=np.uint8)
+    weights = np.array([20, 20, 20, 20, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1], dtype=float)
+    weights /= weights.sum()
+    refs = [bytes(rng.choice(letters, size=int(n), p=weights)) for n in (700, 301, 64)]
+    reads = []
+    for k in range(9):
+        r = refs[k % 3]
+        a = int(rng.integers(0, max(1, len(r) - 60)))
+        reads.append(r[a: a + int(rng.integers(20, 60))])
+    table = np.full(128, 4, dtype=np.int8)
+    for i, c in enumerate("ACGT"):
+        table[ord(c)] = i
+        table[ord(c.lower())] = i
+    table[ord("U")] = table[ord("u")] = 3
+    comp = {ord("A"): "T", ord("a"): "T", ord("C"): "G", ord("c"): "G", ord("G"): "C", ord("g"): "C", ord("T"): "A", ord("t"): "A",
+            ord("U"): "A", ord("u"): "A", ord("N"): "N", ord("n"): "N"}
+    def rc(b):
+        return bytes(ord(comp[c]) if c in comp else 4 for c in reversed(b))
+    def codes(b):
+        return table[np.frombuffer(b, dtype=np.uint8) & 127].astype(np.int8)
+    mat = C.dna_matrix(2, 2)
+    eng.set_sequences_text(reads, refs, table, 5, add_reverse_complement=True)
+    res_t, pool_t = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=15, score_size=2)
+    eng.set_sequences([codes(q) for q in reads] + [codes(rc(q)) for q in reads], [codes(r) for r in refs])
+    res_c, pool_c = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=15, score_size=2)
+    assert len(res_t) == 2 * len(reads) * len(refs)
+    for i in range(len(res_t)):
+        a, b = res_t[i], res_c[i]
+        for k in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag", "cigar_len"):
+            assert int(a[k]) == int(b[k]), (i, k)
+        if a["cigar_len"] > 0:
+            assert list(pool_t[a["cigar_off"]: a["cigar_off"] + a["cigar_len"]]) == list(pool_c[b["cigar_off"]: b["cigar_off"] + b["cigar_len"]])
+    q0 = codes(reads[0]); r0 = codes(refs[0])
+    exp = oracle.align(q0, r0, mat, 5, 3, 1, 0x0f, 0, 32767, 15, 2)
+    assert int(res_t[0]["score1"]) == exp["score1"] and int(res_t[0]["ref_end1"]) == exp["ref_end1"]
+    # a different alphabet size than the one given with the text is refused (no host copy to re-pad from)
+    eng.set_sequences_text(reads, refs, table, 5)
+    with pytest.raises(RuntimeError):
+        eng.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=15, score_size=2)
+    eng.close()

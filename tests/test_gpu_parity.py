@@ -375,3 +375,44 @@ def test_concurrent_callers(ours, checker, capfd):
         q, ref, flag = c
         exp = checker.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, max(15, len(q) // 2), 2)
         assert C.diff_results(g, exp) == [], flag
+
+
+def test_text_sequences_on_device(engine, checker, capfd):
+    """Letters translated, reverse-complemented and padded on the device (ssw_engine_set_sequences_text) against the
+    checker run on host-translated codes: both strands of 60 reads x 3 references, every field and CIGAR word."""
+    rng = np.random.default_rng(777)
+    letters = np.frombuffer(b"ACGTacgtNnUuRY", dtype=np.uint8)
+    w = np.array([24, 24, 24, 24, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1], dtype=float)
+    w /= w.sum()
+    refs = [bytes(rng.choice(letters, size=int(n), p=w)) for n in (20000, 3001, 257)]
+    reads = []
+    for k in range(60):
+        r = refs[k % 3]
+        a = int(rng.integers(0, len(r) - 200))
+        q = bytearray(r[a: a + int(rng.integers(40, 200))])
+        for _ in range(len(q) // 12):
+            q[int(rng.integers(0, len(q)))] = int(rng.choice(letters))
+        reads.append(bytes(q))
+    table = np.full(128, 4, dtype=np.int8)
+    for i, c in enumerate("ACGT"):
+        table[ord(c)] = i
+        table[ord(c.lower())] = i
+    table[ord("U")] = table[ord("u")] = 3
+    comp = {"A": "T", "a": "T", "C": "G", "c": "G", "G": "C", "g": "C", "T": "A", "t": "A", "U": "A", "u": "A", "N": "N", "n": "N"}
+
+    def rc(b):
+        return bytes(ord(comp[chr(c)]) if chr(c) in comp else 4 for c in reversed(b))
+
+    def codes(b):
+        return table[np.frombuffer(b, dtype=np.uint8) & 127].astype(np.int8)
+
+    mat = C.dna_matrix(2, 2)
+    engine.set_sequences_text(reads, refs, table, 5, add_reverse_complement=True)
+    res, pool = engine.align(mat, 5, 3, 1, flag=0x0f, filters=0, filterd=32767, mask_len=20, score_size=2)
+    both = reads + [rc(q) for q in reads]
+    k = 0
+    for q in both:
+        for r in refs:
+            exp = checker.align(codes(q), codes(r), mat, 5, 3, 1, 0x0f, 0, 32767, 20, 2)
+            assert C.diff_results(batch_dict(res, pool, k), exp) == [], k
+            k += 1
