@@ -45,7 +45,6 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inst", type=int, default=-1, help="experiment: force a fill-kernel instance")
     ap.add_argument("--chunk", type=int, default=0, help="experiment: reference chunk length")
-    ap.add_argument("--mode", type=int, default=-1, help="experiment: fill arithmetic (0 all-DPX, 1 biased + IMAD)")
     ap.add_argument("--opt", action="append", default=[], help="experiment: engine option name=value (repeatable)")
     ap.add_argument("--clock-sampler", choices=["smi", "nvml"], default="smi",
                     help="how clocks / throttle reasons are sampled during the timed region")
@@ -244,8 +243,6 @@ def main():
         eng.set_option("inst", args.inst)
     if args.chunk:
         eng.set_option("chunk", args.chunk)
-    if args.mode >= 0:
-        eng.set_option("mode", args.mode)
     for kv in args.opt:
         name, val = kv.split("=")
         eng.set_option(name, int(val))

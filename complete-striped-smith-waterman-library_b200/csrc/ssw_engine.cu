@@ -49,7 +49,6 @@ struct Inst { int G, R; };
 static const Inst kInst[] = {
 	{8, 4}, {8, 5}, {8, 8}, {8, 10}, {8, 16}, {8, 20}, {16, 16}, {16, 20}, {32, 16}, {32, 20},      /* 0..9: forward, by rows */
 	{32, 4}, {32, 5}, {32, 8}, {32, 10},                                                            /* 10..13: reverse only (one alignment per warp) */
-	{16, 10}, {32, 10},                                                                             /* 14, 15: experiment instances ("inst" option) */
 };
 static const int kNumFwd = 10;
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
@@ -57,10 +56,10 @@ static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 static int g_strip_parts = 0;      /* "parts" option: 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
 static int g_strip_super = SSW_STRIP_SUPER;   /* columns per super-block of the strip kernel ("super" option, tests) */
 static int g_grid_min_pairs = 32768;    /* "grid_min" option: smaller grids use the general path */
-static int g_force_inst = -1;      /* experiment knob ("inst" option): use this instance whenever it covers the query */
+static int g_force_inst = -1;      /* "inst" option (measurements): use this forward instance whenever it covers the query */
 static int pick_inst(int lp)
 {
-	if (g_force_inst >= 0 && g_force_inst < kNumInst && kInst[g_force_inst].G * kInst[g_force_inst].R >= lp) return g_force_inst;
+	if (g_force_inst >= 0 && g_force_inst < kNumFwd && kInst[g_force_inst].G * kInst[g_force_inst].R >= lp) return g_force_inst;
 	for (int i = 0; i < kNumFwd; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
 	return -1;
 }
@@ -170,8 +169,6 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, i
 	case 11: rc = launch_fill<32, 5>(this, n_items, dir, share, P); break;
 	case 12: rc = launch_fill<32, 8>(this, n_items, dir, share, P); break;
 	case 13: rc = launch_fill<32, 10>(this, n_items, dir, share, P); break;
-	case 14: rc = launch_fill<16, 10>(this, n_items, dir, share, P); break;
-	case 15: rc = launch_fill<32, 10>(this, n_items, dir, share, P); break;
 	default: break;
 	}
 	tr.lap("  fill: launch");
@@ -209,8 +206,6 @@ static int fill_occupancy(int inst, int n)
 	case 7: occ = fill_occ_of<16, 20>(n); break;
 	case 8: occ = fill_occ_of<32, 16>(n); break;
 	case 9: occ = fill_occ_of<32, 20>(n); break;
-	case 14: occ = fill_occ_of<16, 10>(n); break;
-	case 15: occ = fill_occ_of<32, 10>(n); break;
 	default: break;
 	}
 	cache[inst][n] = occ > 0 ? occ : 1;
@@ -267,7 +262,6 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }       /* index into kInst */
 	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 7) / 8 * 8 : SSW_STRIP_SUPER; return 0; }
 	if (!strcmp(name, "tb_maxbw")) { g_ssw_tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
-	if (!strcmp(name, "mode")) return 0;      /* retired experiment (biased arithmetic with IMAD adds was slower, profiles/fill_kernel_r1.md) */
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;
 }
