@@ -475,10 +475,11 @@ static int resolve_forward(ssw_engine* e, std::vector<SswAlnDesc>& descs, const 
 /* strip-pipelined fill for queries longer than one strip (ssw_fill_strips_kernel)               */
 /* ------------------------------------------------------------------------------------------- */
 
-struct StripReq {             /* one pair-task (forward) or one alignment (reverse) for the strip kernel */
+struct StripReq {             /* one pair-task for the strip kernel */
 	int64_t a, b;             /* indices into alns; b = -1: half B dead */
 	SswQuery qa, qb;
-	int32_t r, cend, p1, term;
+	int32_t r, cend, p1, term;            /* forward: common reference r, p1 = its length; reverse: half A's window */
+	int32_t r_b, cend_b, p1_b, term_b;    /* reverse: half B's reference, end column, scan length, score */
 };
 
 /* Launch the strip kernel over `reqs`; every launch hands its descriptors to `after` (resolve + merge). */
@@ -545,11 +546,16 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 			memset(&T, 0, sizeof(T));
 			T.qa = q.qa; T.qb = q.qb;
 			T.ref_off = e->r_off[q.r]; T.ref_len = e->r_len[q.r]; T.cend = q.cend; T.p1 = q.p1; T.term_a = q.term;
+			T.p1_a = q.p1; T.term_b = -1; T.ref_off_b = T.ref_off; T.cend_b = q.cend; T.p1_b = 0;
+			if (dir < 0 && q.b >= 0) {
+				T.ref_off_b = e->r_off[q.r_b]; T.cend_b = q.cend_b; T.p1_b = q.p1_b; T.term_b = q.term_b;
+				T.p1 = std::max(q.p1, q.p1_b);
+			}
 			T.n_strips = n_strips;
 			T.super = g_strip_super;
-			T.n_super = term ? std::max(1, (q.p1 + T.super - 1) / T.super) : 1;
-			T.bnd_len = ((q.p1 + 7) / 8 * 8) + 2 * SSW_STRIP_BPAD + 64;
-			const size_t need = 4 * (cm_words + bnd_words + park_words + 6 * (size_t)T.bnd_len + (size_t)q.p1 + 8);
+			T.n_super = term ? std::max(1, (T.p1 + T.super - 1) / T.super) : 1;
+			T.bnd_len = ((T.p1 + 7) / 8 * 8) + 2 * SSW_STRIP_BPAD + 64;
+			const size_t need = 4 * (cm_words + bnd_words + park_words + 6 * (size_t)T.bnd_len + (size_t)T.p1 + 8);
 			if (!tasks.empty() && need > budget) break;
 			T.cm_off = dir > 0 ? (int64_t)cm_words : -1;
 			T.bnd_off = (int64_t)bnd_words;
@@ -563,7 +569,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 				SswAlnDesc d;
 				memset(&d, 0, sizeof(d));
 				d.first_item = n_best; d.n_items = n_strips * T.n_super; d.half = h;
-				d.ref_len = dir > 0 ? T.ref_len : q.p1;
+				d.ref_len = dir > 0 ? T.ref_len : (h ? q.p1_b : q.p1);
 				d.read_len = h ? q.qb.len : q.qa.len;
 				d.word = 1; d.limit = 0x7fffffff; d.mask_len = X.mask_len; d.cm_off = T.cm_off; d.scan_all = 1;
 				descs.push_back(d);
@@ -586,7 +592,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		gsync[0] = 0;
 		if (e->d_sync.ensure(sizeof(int) * gsync.size())) return -1;
 		SSW_CUDA_OK(cudaMemcpyAsync(e->d_sync.p, gsync.data(), sizeof(int) * gsync.size(), cudaMemcpyHostToDevice, e->stream));
-		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 2);
+		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 4);
 		tr.lap("strips: h2d + memset");
 		e->t_k.start(e->stream);
 #define SSW_STRIPS_GO(DIR, TERM, SPLIT)                                                                                 \
@@ -859,14 +865,30 @@ static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	struct Key { int inst; int64_t idx; };
 	std::vector<Key> keys;
 	std::vector<StripReq> long_reqs;
+	std::vector<int64_t> long_sel;
 	for (size_t i = 0; i < sel.size(); ++i) {
 		const Aln& a = alns[sel[i]];
 		const int inst = pick_inst_g32(lp_of(a.fwd.read + 1, a.word));
 		if (inst >= 0) { keys.push_back(Key{inst, sel[i]}); continue; }
+		long_sel.push_back(sel[i]);
+	}
+	/* long queries: two alignments per strip task (they need not share a reference: half B has its own letter stream),
+	 * partners of similar padded length so that neither half drags many dead strips along */
+	std::sort(long_sel.begin(), long_sel.end(), [&](int64_t x, int64_t y) {
+		const int lx = lp_of(alns[x].fwd.read + 1, alns[x].word), ly = lp_of(alns[y].fwd.read + 1, alns[y].word);
+		return lx != ly ? lx > ly : x < y;
+	});
+	for (size_t i = 0; i < long_sel.size(); i += 2) {
+		const Aln& a = alns[long_sel[i]];
 		StripReq q;
 		memset(&q, 0, sizeof(q));
-		q.a = sel[i]; q.b = -1; q.r = a.r; q.cend = a.fwd.ref; q.p1 = a.fwd.ref + 1; q.term = a.fwd.score;
+		q.a = long_sel[i]; q.b = -1; q.r = a.r; q.cend = a.fwd.ref; q.p1 = a.fwd.ref + 1; q.term = a.fwd.score;
 		q.qa.off = (int32_t)e->q_off[a.q]; q.qa.len = a.fwd.read + 1; q.qa.lp = lp_of(q.qa.len, a.word); q.qa.rev = 1;
+		if (i + 1 < long_sel.size()) {
+			const Aln& b = alns[long_sel[i + 1]];
+			q.b = long_sel[i + 1]; q.r_b = b.r; q.cend_b = b.fwd.ref; q.p1_b = b.fwd.ref + 1; q.term_b = b.fwd.score;
+			q.qb.off = (int32_t)e->q_off[b.q]; q.qb.len = b.fwd.read + 1; q.qb.lp = lp_of(q.qb.len, b.word); q.qb.rev = 1;
+		}
 		long_reqs.push_back(q);
 	}
 	auto merge = [&](const std::vector<SswAlnDesc>& descs, const std::vector<int64_t>& desc_aln) -> int {

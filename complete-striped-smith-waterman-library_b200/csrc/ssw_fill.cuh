@@ -448,8 +448,13 @@ struct SswStripTask {
 	int32_t bnd_len;       /* words per boundary array: multiple of 4, >= p1 + 2*SSW_STRIP_BPAD + 8 */
 	int32_t first_best;    /* record of (strip s, super-block b) = first_best + s * n_super + b */
 	int64_t park_off;      /* parked lane registers: n_strips x 32 lanes x (2R + 3) words */
-	int32_t super;         /* columns per super-block (multiple of 4) */
-	int32_t pad_;
+	int32_t super;         /* columns per super-block (multiple of 8) */
+	int32_t term_b;        /* reverse pass, half B: terminate score, else -1 */
+	/* reverse pass: the two alignments of a task are unrelated (own reference window, own end column), so half B has
+	 * its own letter stream; p1 above is the larger of the two scan ranges */
+	int64_t ref_off_b;
+	int32_t cend_b, p1_b;
+	int32_t p1_a, pad_;
 };
 
 #ifdef SSW_CPU_EMU
@@ -510,12 +515,15 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 	/* shared memory: NW profiles, then prog[n_strips], then the stop flag */
 	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
 	volatile int* prog = reinterpret_cast<volatile int*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R);
-	volatile int* stop = prog + T.n_strips;
+	volatile int* stop = prog + T.n_strips;                /* 1: every requested half has met its score (reverse pass) */
+	volatile int* done = stop + 1;                          /* bit h: half h has met its score */
+	const int need_mask = (T.term_a >= 0 ? 1 : 0) | (T.term_b >= 0 ? 2 : 0);
 	for (int i = threadIdx.x; i < T.n_strips; i += blockDim.x) prog[i] = -0x40000000;
-	if (threadIdx.x == 0) *stop = 0;
+	if (threadIdx.x == 0) { *stop = 0; *done = 0; }
 	__syncthreads();
 
 	const uint8_t* rp = reinterpret_cast<const uint8_t*>(refs) + T.ref_off;
+	const uint8_t* rpB = reinterpret_cast<const uint8_t*>(refs) + (DIR < 0 ? T.ref_off_b : T.ref_off);
 	const uint32_t negO = pack2(-gapO, -gapO), negE = pack2(-gapE, -gapE);
 	const int col_hi = T.ref_len + SSW_REF_PAD - 8, col_lo = -SSW_REF_PAD + 7;
 	const ssw_saddr pbase = ssw_sadd(ssw_sbase(prof), lane * 4);
@@ -559,6 +567,8 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 			int col = DIR > 0 ? sp0 : T.cend - sp0;
 			if (DIR > 0) col = min(col, col_hi); else col = max(col, col_lo);
 			const uint8_t* lptr = rp + col;
+			int colB = DIR < 0 ? max(T.cend_b - sp0, col_lo) : 0;      /* reverse pass: half B's own letter cursor */
+			const uint8_t* lptrB = rpB + colB;
 			bool stopped = false;
 			int known = -0x40000000, ahead = -0x40000000;       /* progress of the producing CTA as last read (s == s_first only) */
 			uint32_t top_keep = lane == 0 ? 0u : 1u;
@@ -623,6 +633,15 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 						if (DIR < 0) { if (sp0 + 4 * h + j < 0) letter = n; }   /* right of cend; forward scans start inside the null pad */
 						uint32_t sc[R], Hn[R];
 						ssw_load_scores<R>(sc, pbase, ptail, letter);
+						if (DIR < 0) {
+							/* half B reads its own reference: its scores come from the profile row of its own letter */
+							int letterB = (int)lptrB[-(4 * h + j)];
+							if (sp0 + 4 * h + j < 0) letterB = n;
+							uint32_t sb[R];
+							ssw_load_scores<R>(sb, pbase, ptail, letterB);
+#pragma unroll
+							for (int k = 0; k < R; ++k) sc[k] = (sc[k] & 0x0000ffffu) | (sb[k] & 0xffff0000u);
+						}
 						uint32_t own;
 						ssw_cells<R>(Hd, E, sc, Hn, inH, inF, inC, negO, negE, outH, outF, outC, own);
 						cmv[j] = outC; hv[j] = outH; fv[j] = outF;
@@ -641,10 +660,12 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 						}
 					}
 					if (TERM && s + 1 == T.n_strips) {
-						if (lane == 31 && T.term_a >= 0) {
+						if (lane == 31) {
 #pragma unroll
-							for (int j = 0; j < 4; ++j)
-								if (g + j >= 0 && g + j < T.p1 && half_of(cmv[j], 0) == T.term_a) hit = 1;
+							for (int j = 0; j < 4; ++j) {
+								if (g + j >= 0 && g + j < T.p1_a && half_of(cmv[j], 0) == T.term_a) hit |= 1;
+								if (g + j >= 0 && g + j < T.p1_b && half_of(cmv[j], 1) == T.term_b) hit |= 2;
+							}
 						}
 					}
 				}
@@ -659,13 +680,20 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 					}
 				}
 				if (TERM && s + 1 == T.n_strips) {
-					if (__any_sync(FULL, hit)) { if (lane == 0) *stop = 1; stopped = true; break; }
+					const int hm = (__any_sync(FULL, hit & 1) ? 1 : 0) | (__any_sync(FULL, hit & 2) ? 2 : 0);
+					if (hm) {
+						int d = 0;
+						if (lane == 0) { d = *done | hm; *done = d; if (d == need_mask) *stop = 1; }
+						d = __shfl_sync(FULL, d, 0);
+						if (d == need_mask) { stopped = true; break; }
+					}
 				}
 				sp0 += 8;
 				{
 					const int ncol = DIR > 0 ? min(col + 8, col_hi) : max(col - 8, col_lo);
 					lptr += ncol - col;
 					col = ncol;
+					if (DIR < 0) { const int nb_ = max(colB - 8, col_lo); lptrB += nb_ - colB; colB = nb_; }
 				}
 			}
 

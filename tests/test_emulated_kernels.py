@@ -106,6 +106,21 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
             got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
             assert C.diff_results(got, exp) == [], (flag, parts, i)
     eng.set_option("parts", 0)
+    # reverse pass with two unrelated alignments per strip task: different references, end columns and scan lengths
+    ref2 = np.concatenate([rng.integers(0, 4, size=700).astype(np.int8), ref[900:1500], rng.integers(0, 4, size=150).astype(np.int8)])
+    refs2 = [ref, ref2, ref[:900].copy()]
+    eng.set_sequences(reads, refs2)
+    for flag in (8, 2):
+        res, pool = eng.align(mat, 5, 3, 1, flag=flag, filterd=32767, mask_len=100, score_size=2)
+        k = 0
+        for q in reads:
+            for rr in refs2:
+                exp = oracle.align(q, rr, mat, 5, 3, 1, flag, 0, 32767, 100, 2)
+                r = res[k]
+                got = {f: int(r[f]) for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
+                got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
+                assert C.diff_results(got, exp) == [], (flag, k)
+                k += 1
     eng.set_option("super", 0)
     eng.close()
 
