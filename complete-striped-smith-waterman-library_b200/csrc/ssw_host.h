@@ -3,6 +3,8 @@
 #define SSW_HOST_H
 
 #include <string.h>
+#include <algorithm>
+#include <thread>
 #include "ssw_common.cuh"
 
 /* counts device allocations and frees made through SswDevBuf: the engine re-reads the free device memory only when
@@ -75,7 +77,18 @@ struct SswStagedD2H {
 			if (k > 0) {
 				const size_t j = k - 1, len = j + 1 < n ? CHUNK : bytes - j * CHUNK;
 				if (cudaEventSynchronize(ev[j & 1]) != cudaSuccess) return -1;
-				memcpy((char*)dst + j * CHUNK, pin[j & 1], len);
+				/* the destination is often freshly allocated memory: four threads share the copy (and its page faults) */
+				char* d = (char*)dst + j * CHUNK;
+				const char* sp = (const char*)pin[j & 1];
+				const size_t q = (len / 4 + 4095) & ~(size_t)4095;
+				std::thread th[3];
+				int nt = 0;
+				for (int t = 1; t < 4 && (size_t)t * q < len; ++t, ++nt) {
+					const size_t o = (size_t)t * q, l = std::min(q, len - o);
+					th[nt] = std::thread([=]() { memcpy(d + o, sp + o, l); });
+				}
+				memcpy(d, sp, std::min(q, len));
+				for (int t = 0; t < nt; ++t) th[t].join();
 			}
 		}
 		return 0;
