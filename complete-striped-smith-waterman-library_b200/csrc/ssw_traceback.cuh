@@ -158,7 +158,7 @@ template <int NT>
 __device__ static __forceinline__ void ssw_tb_tiles(const bool (&act)[NT], int i, const int (&j)[NT], int beg, int lane,
                                                    const int (&Hup)[NT], const int (&Eup)[NT], const int (&Hdg)[NT], const int (&s)[NT],
                                                    int gapO, int gapE, int g, int& carryF, int& carryH, int& carryFp,
-                                                   int (&Hv)[NT], int (&Ev)[NT], int (&dirb)[NT])
+                                                   int (&Hv)[NT], int (&Ev)[NT], int (&dirb)[NT], int span)
 {
 	constexpr unsigned FULL = 0xffffffffu;
 	int de3[NT], e1[NT], T2[NT], Y[NT], P[NT];
@@ -173,8 +173,11 @@ __device__ static __forceinline__ void ssw_tb_tiles(const bool (&act)[NT], int i
 		Y[t] = e1[t] > T2[t] ? e1[t] : T2[t];
 		P[t] = act[t] ? Y[t] - gapO : SSW_TB_NEGINF;
 	}
+	/* `span` active lanes (warp-uniform): distances of span and more cannot contribute, so a narrow band row needs
+	 * fewer than five levels of the scan */
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
+		if (d >= span) break;
 #pragma unroll
 		for (int t = 0; t < NT; ++t) {
 			const int o = __shfl_up_sync(FULL, P[t], d);
@@ -234,7 +237,8 @@ __device__ static __forceinline__ void ssw_tb_row_group(int i, int j0, int beg, 
 			s[t] = (int)smat[(int)ref[j[t]] * n + rd];
 		}
 	}
-	ssw_tb_tiles<NT>(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryH, carryFp, Hv, Ev, dirb);
+	ssw_tb_tiles<NT>(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryH, carryFp, Hv, Ev, dirb,
+	                 NT == 1 ? min(32, end - j0 + 1) : 32);
 #pragma unroll
 	for (int t = 0; t < NT; ++t) {
 		if (act[t]) {
