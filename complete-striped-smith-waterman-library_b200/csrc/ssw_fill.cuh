@@ -45,6 +45,9 @@
 #define SSW_STRIP_R 10                      /* rows per lane of the strip kernel: 320 rows per strip (config 5: R=10 247 ms, 16: 268, 20: 257, 8: 365) */
 #endif
 #define SSW_STRIP_MAXW 16                   /* warps per CTA of the strip kernel */
+#ifndef SSW_FLOOR_PERIOD
+#define SSW_FLOOR_PERIOD 1                   /* loop bodies between refreshes of the group floor of the best-cell bookkeeping */
+#endif
 #define SSW_STRIP_LAG 48                    /* a strip's last lane ends a super-block this many columns before the strip above */
 #define SSW_STRIP_SUPER 4096                /* columns per super-block (granularity of early termination) */
 #define SSW_STRIP_BPAD 32                   /* words in front of every boundary array (scan positions down to -32) */
@@ -351,7 +354,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 
 	for (int body = 0; body < n_body; ++body) {
 		uint32_t cmv[U];
-		if ((body & 1) == 0) {
+		if ((body & (SSW_FLOOR_PERIOD - 1)) == 0) {
 			/* lower bound of the group's final maximum: a lane value below it can never be the best cell, so the lane's
 			 * running best is raised to (bound - 1) and such values no longer trigger the bookkeeping */
 			const uint32_t floor2 = ssw_group_max<G>(lb.best);
