@@ -10,6 +10,7 @@ Reference interface mirrored by the bindings: src/ssw.h:55-66 (s_align),
 import ctypes as ct
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -114,7 +115,8 @@ _built = {}
 def build_oracle():
     """Compile the checkers (oracle restatement; the reference too when its tree is present)."""
     if "oracle" not in _built:
-        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "all"], check=True)
+        # make's chatter goes to stderr: bench.py prints exactly one JSON line on stdout
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "all"], check=True, stdout=sys.stderr)
         _built["oracle"] = True
 
 
