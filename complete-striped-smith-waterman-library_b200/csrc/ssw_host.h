@@ -53,10 +53,13 @@ inline size_t ssw_free_device_bytes()
 /* Large device -> pageable-host copies: a plain cudaMemcpy into pageable memory runs at a few GB/s (the driver stages
  * it through one small pinned buffer).  This stages through two pinned 8 MB buffers: the copy of chunk k+1 runs while the
  * host moves chunk k to its destination. */
+#ifndef SSW_D2H_CHUNK
+#define SSW_D2H_CHUNK ((size_t)8 << 20)      /* the emulator build uses a tiny value so that CPU tests cross chunk borders */
+#endif
 struct SswStagedD2H {
 	void* pin[2] = {nullptr, nullptr};
 	cudaEvent_t ev[2] = {nullptr, nullptr};
-	static constexpr size_t CHUNK = (size_t)8 << 20;
+	static constexpr size_t CHUNK = SSW_D2H_CHUNK;
 	int copy(void* dst, const void* src_dev, size_t bytes, cudaStream_t st)
 	{
 		if (bytes < 2 * CHUNK) {
