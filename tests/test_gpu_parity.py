@@ -416,3 +416,26 @@ def test_text_sequences_on_device(engine, checker, capfd):
             exp = checker.align(codes(q), codes(r), mat, 5, 3, 1, 0x0f, 0, 32767, 20, 2)
             assert C.diff_results(batch_dict(res, pool, k), exp) == [], k
             k += 1
+
+
+def test_large_result_array_staged_copy(engine, checker, capfd):
+    """A grid whose records exceed the staged-copy threshold (2 x 8 MB): 520,000 pairs of short sequences; pairs sampled
+    across every staging chunk are compared with the checker and the whole array with a second, independent call."""
+    rng = np.random.default_rng(86420)
+    refs = [rng.integers(0, 4, size=int(rng.integers(40, 70)), dtype=np.int8) for _ in range(5200)]
+    queries = [rng.integers(0, 4, size=int(rng.integers(24, 40)), dtype=np.int8) for _ in range(100)]
+    mat = C.dna_matrix(2, 2)
+    engine.set_sequences(queries, refs)
+    res, _ = engine.align(mat, 5, 3, 1, flag=0, mask_len=15, score_size=2)
+    assert res.nbytes > 2 * (8 << 20)
+    pq = np.repeat(np.arange(100, dtype=np.int32), 5200)
+    pr = np.tile(np.arange(5200, dtype=np.int32), 100)
+    res2, _ = engine.align(mat, 5, 3, 1, flag=0, mask_len=15, score_size=2, pair_query=pq, pair_ref=pr)   # general path, explicit pairs
+    for f in ("score1", "score2", "ref_end1", "read_end1", "ref_end2"):
+        assert (res[f] == res2[f]).all(), f
+    for p in range(0, len(res), 4999):
+        q, r = queries[p // 5200], refs[p % 5200]
+        exp = checker.align(q, r, mat, 5, 3, 1, 0, 0, 0, 15, 2)
+        got = {k: int(res[p][k]) for k in FIELDS8}
+        got["cigar"] = []
+        assert C.diff_results(got, exp) == [], p
