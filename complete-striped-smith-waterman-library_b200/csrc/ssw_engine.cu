@@ -94,7 +94,7 @@ struct ssw_engine {
 	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out, d_sync;
 	SswStagedD2H staged;
 	int64_t opt_chunk = 0;
-	int64_t opt_small_chunk = 0;        /* experiment: chunk length of launches too small to fill the device */
+	int64_t opt_small_chunk = 0;        /* "small_chunk" option (measurements): chunk length of launches too small to fill the device */
 	ssw_engine_timing timing;
 	SswTimer t_total, t_k;
 
@@ -528,8 +528,8 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 				const double rounds = (double)((per + wbest - 1) / wbest);
 				const double waves = ceil((double)(n_same * pp) / (double)e->sm_count);
 				/* a CTA with few warps does not fill an SM: charge it as if it had at least 8 */
-				/* measured: a split CTA needs 8 % longer per round than an unsplit one (config 5: 32.7 vs 30.2 ms) */
-				const double cost = waves * rounds * (wbest < 8 ? 8.0 / wbest : 1.0) * (pp > 1 ? 1.08 : 1.0);
+				/* measured: a split CTA needs ~4 % longer per round than an unsplit one (config 5: 29.1 vs 28.0 ms) */
+				const double cost = waves * rounds * (wbest < 8 ? 8.0 / wbest : 1.0) * (pp > 1 ? 1.04 : 1.0);
 				if (cost < best_cost - 1e-9) { best_cost = cost; parts = pp; nw = wbest; }
 			}
 		}
@@ -761,8 +761,12 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				if (P.gap_extend > 0 && S.max_mat > 0) {
 					warm = (int64_t)max_lp + ((int64_t)max_len * S.max_mat + P.gap_extend - 1) / P.gap_extend + 4;
 					warm = (warm + 3) / 4 * 4;
-					chunk = e->opt_chunk > 0 ? e->opt_chunk : (e->opt_small_chunk > 0 && base_chunk < 4096) ? std::max<int64_t>(e->opt_small_chunk, 2 * warm)
-					      : std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
+					/* a launch too small to fill the device (one ssw_align call, the word re-fill of a few overflowed reads) is
+					 * latency-bound: shorter chunks, at the price of more warm-up columns (measured on config 2's re-fill
+					 * launch: 4.07 ms with the 16 x warm-up rule, 3.6 ms with 6 x) */
+					if (e->opt_chunk > 0) chunk = e->opt_chunk;
+					else if (base_chunk < 4096) chunk = e->opt_small_chunk > 0 ? std::max<int64_t>(e->opt_small_chunk, 2 * warm) : std::max<int64_t>(2048, 6 * warm);
+					else chunk = std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
 				}
 				int64_t n_chunks = chunk >= ref_len ? 1 : (ref_len + chunk - 1) / chunk;
 				if (n_chunks > 1 && e->opt_chunk == 0) {
