@@ -128,8 +128,7 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw
 #define SSW_FILL_GO(DIR, CM, TERM)                                                                               \
 	do {                                                                                                         \
 		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM>;                                                        \
-		if (smem > 48 * 1024)                                                                                    \
-			SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+		if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem)) return -1;                           \
 		ssw_launch(kern, dim3(grid), dim3(warps * 32), smem, e->stream, items, n_items, q, r, mat, (int)P.n,     \
 		           (int)P.gap_open, (int)P.gap_extend, cm, bests, share);                                        \
 	} while (0)
@@ -185,7 +184,7 @@ static int fill_occ_of(int n)
 	int occ = 0;
 	const size_t smem = ssw_fill_smem_bytes<R>(n, 1);
 	auto kern = ssw_fill_kernel<G, R, 1, true, false>;
-	if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSW_FILL_THREADS, smem) != cudaSuccess) occ = 1;
 	return occ;
 }
@@ -294,8 +293,9 @@ int ssw_engine::upload_refs(int n)
 	std::vector<int8_t> padded((size_t)total, (int8_t)n);
 	for (int i = 0; i < n_r; ++i) memcpy(padded.data() + r_off[i], h_r.data() + h_r_off[i], (size_t)r_len[i]);
 	if (d_r.ensure((size_t)total)) return -1;
+	/* pageable source: the call returns once the bytes sit in the driver's staging buffer, so `padded` may go away and
+	 * later work on the stream is ordered behind the copy -- no synchronisation needed */
 	SSW_CUDA_OK(cudaMemcpyAsync(d_r.p, padded.data(), (size_t)total, cudaMemcpyHostToDevice, stream));
-	SSW_CUDA_OK(cudaStreamSynchronize(stream));
 	padded_n = n;
 	return 0;
 }
@@ -317,7 +317,6 @@ extern "C" int ssw_engine_set_sequences(ssw_engine* e,
 	if (e->d_q.ensure(e->h_q.size() + 16)) return -1;
 	SSW_CUDA_OK(cudaMemcpyAsync(e->d_q.p, e->h_q.data(), e->h_q.size(), cudaMemcpyHostToDevice, e->stream));
 	e->padded_n = -1;           /* the null letter depends on the alphabet size given at align time */
-	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
 	return 0;
 }
 
@@ -598,7 +597,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 #define SSW_STRIPS_GO(DIR, TERM, SPLIT)                                                                                 \
 		do {                                                                                                            \
 			auto kern = ssw_fill_strips_kernel<SSW_STRIP_R, DIR, TERM, SPLIT>;                                          \
-			if (smem > 48 * 1024) SSW_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+			if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem)) return -1;                              \
 			ssw_launch(kern, dim3((unsigned)(tasks.size() * (size_t)parts)), dim3(nw * 32), smem, e->stream, (const SswStripTask*)e->d_items.as<SswStripTask>(), \
 			           (const int8_t*)e->d_q.as<int8_t>(), (const int8_t*)e->d_r.as<int8_t>(), (const int8_t*)e->d_mat.as<int8_t>(), (int)P.n, \
 			           (int)P.gap_open, (int)P.gap_extend, e->d_colmax.as<uint32_t>(), e->d_bnd.as<uint32_t>(), e->d_park.as<uint32_t>(), \

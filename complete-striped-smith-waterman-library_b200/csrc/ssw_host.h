@@ -4,7 +4,10 @@
 
 #include <string.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <thread>
+#include <utility>
 #include "ssw_common.cuh"
 
 /* counts device allocations and frees made through SswDevBuf: the engine re-reads the free device memory only when
@@ -32,6 +35,23 @@ struct SswDevBuf {
 	void release() { ++ssw_alloc_epoch(); if (p) cudaFree(p); p = nullptr; cap = 0; }
 	template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+/* opt a kernel into more than 48 KB of dynamic shared memory, once per (device, kernel, size): the attribute call costs
+ * microseconds that a one-pair ssw_align would otherwise pay on every launch */
+inline int ssw_ensure_dyn_smem(const void* fn, size_t smem)
+{
+	if (smem <= 48 * 1024) return 0;
+	static std::mutex mu;
+	static std::map<std::pair<int, const void*>, size_t> granted;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	std::lock_guard<std::mutex> lock(mu);
+	size_t& have = granted[std::make_pair(dev, fn)];
+	if (have >= smem) return 0;
+	if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+	have = smem;
+	return 0;
+}
 
 /* free memory of the current device, re-read only after one of our buffers was (re)allocated */
 inline size_t ssw_free_device_bytes()

@@ -569,7 +569,7 @@ static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
 			const dim3 grid((cnt + SSW_TB_WARPS - 1) / SSW_TB_WARPS);
 			if (ring) {
 				const size_t smem = (size_t)SSW_TB_WARPS * 4 * (size_t)ring * sizeof(int32_t) + (size_t)n * n + 16;
-				if (smem > 48 * 1024) SSW_CUDA_OK(cudaFuncSetAttribute(ssw_banded_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(ssw_banded_smem_kernel), smem)) return -1;
 				ssw_launch(ssw_banded_smem_kernel, grid, dim3(SSW_TB_THREADS), smem, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE, base, d_cig, ring);
 			} else {
 				ssw_launch(ssw_banded_kernel, grid, dim3(SSW_TB_THREADS), 0, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE,

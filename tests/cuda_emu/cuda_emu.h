@@ -240,6 +240,7 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent
 #define cudaStreamNonBlocking 1
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+static inline cudaError_t cudaFuncSetAttribute(const void*, int, int) { return cudaSuccess; }
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 4; return cudaSuccess; }
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = (size_t)4 << 30; *t = (size_t)8 << 30; return cudaSuccess; }
 
