@@ -56,6 +56,7 @@ static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 static int g_strip_parts = 0;      /* "parts" option: 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
 static int g_strip_super = SSW_STRIP_SUPER;   /* columns per super-block of the strip kernel ("super" option, tests) */
 static int g_grid_min_pairs = 32768;    /* "grid_min" option: smaller grids use the general path */
+static int64_t g_latency_cols = 1 << 20;   /* "latency_cols" option: passes over at most this many reference columns use the 32-lane instances */
 static int g_force_inst = -1;      /* "inst" option (measurements): use this forward instance whenever it covers the query */
 static int pick_inst(int lp)
 {
@@ -254,6 +255,7 @@ extern "C" const char* ssw_engine_device_name(const ssw_engine* e) { return e ? 
 extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value)
 {
 	if (!e || !name) return -1;
+	if (!strcmp(name, "latency_cols")) { g_latency_cols = value < 0 ? 0 : value; return 0; }
 	if (!strcmp(name, "parts")) { g_strip_parts = value == 1 || value == 2 || value == 4 ? (int)value : 0; return 0; }
 	if (!strcmp(name, "small_chunk")) { e->opt_small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
@@ -630,10 +632,18 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	const int limit = word ? S.limit_word : S.limit_byte;
 	struct Key { int inst; int32_t r; int32_t q; int32_t lp; int64_t idx; };
 	std::vector<Key> keys, long_keys;          /* long_keys: queries longer than one strip */
+	/* A pass over few columns cannot fill the device whatever its layout, so its duration is the latency of one group's
+	 * sweep: prefer 32 lanes with few rows each (a step is a chain of R dependent cell updates: (32,5) sweeps a 150 bp
+	 * query ~4x faster than (8,20), which is the better shape once there is enough work).  This is what a one-pair
+	 * ssw_align call gets. */
+	int64_t pass_cols = 0;
+	for (size_t i = 0; i < sel.size() && pass_cols <= g_latency_cols; ++i) pass_cols += alns[sel[i]].ref_len;
+	const bool latency = g_force_inst < 0 && pass_cols <= g_latency_cols;
 	for (size_t i = 0; i < sel.size(); ++i) {
 		const Aln& a = alns[sel[i]];
 		const int lp = lp_of(a.read_len, word);
-		const int inst = pick_inst(lp);
+		int inst = latency ? pick_inst_g32(lp) : -1;
+		if (inst < 0) inst = pick_inst(lp);
 		(inst < 0 ? long_keys : keys).push_back(Key{inst < 0 ? 0 : inst, a.r, a.q, lp, sel[i]});
 	}
 	auto by_ref = [](const Key& x, const Key& y) {

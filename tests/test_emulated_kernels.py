@@ -36,6 +36,7 @@ def oracle():
 
 
 def test_emulated_goldens(emu, capfd):
+    _latency_instances(True)
     with open(os.path.join(C.GOLDEN, "goldens.json")) as f:
         goldens = json.load(f)
     for case in goldens:
@@ -45,16 +46,28 @@ def test_emulated_goldens(emu, capfd):
         assert run_golden(emu, case, limit) == []
 
 
-def test_emulated_random_vs_oracle(emu, oracle, capfd):
-    rng = np.random.default_rng(424242)
+def _latency_instances(on):
+    """Small passes use the 32-lane kernel instances ("latency_cols" option, process-wide); off = the layouts a large
+    batch gets, so that the small CPU cases cover both families."""
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", (1 << 20) if on else 0)
+    eng.close()
+
+
+@pytest.mark.parametrize("latency", [True, False])
+def test_emulated_random_vs_oracle(emu, oracle, latency, capfd):
+    _latency_instances(latency)
+    rng = np.random.default_rng(424242 + int(latency))
     bad = []
     n = 0
-    while n < 150:
+    while n < 110:
         c = random_case(rng)           # every gap regime, incl. gapO <= gapE (lane-literal kernel)
         n += 1
         d = C.diff_results(emu.align(**c), oracle.align(**c))
         if d:
             bad.append((n, d))
+    _latency_instances(False)          # the remaining tests of this module exercise the batch layouts
     assert bad == []
 
 
