@@ -121,7 +121,17 @@ typedef struct {
 } ssw_engine_timing;
 int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t);
 
-/* Tuning knobs, mostly for tests: "chunk" (reference chunk length in columns, 0 = automatic). */
+/*
+ * Tuning knobs for tests and measurements; none of them changes a result.  Unknown names return -1.
+ *   "chunk"         reference chunk length in columns of the fill kernel (0 = automatic)
+ *   "small_chunk"   the same for launches too small to fill the device (0 = automatic)
+ *   "inst"          force forward kernel instance i (rows-per-lane / lanes-per-group table of the engine; -1 = automatic)
+ *   "latency_cols"  passes over at most this many reference columns use the 32-lane instances (0 = never; process-wide)
+ *   "parts"         CTAs per task of the strip-pipelined kernel: 0 automatic, 1 never split, 2 / 4 forced (process-wide)
+ *   "super"         columns per super-block of the strip-pipelined kernel (process-wide)
+ *   "grid_min"      smallest full score-only grid that is planned on the device (process-wide)
+ *   "tb_maxbw"      widest band handled by the shared-memory traceback kernel (process-wide)
+ */
 int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value);
 
 #ifdef __cplusplus
