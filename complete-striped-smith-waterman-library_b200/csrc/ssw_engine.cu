@@ -94,6 +94,7 @@ struct ssw_engine {
 	/* scratch */
 	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out, d_sync;
 	SswStagedD2H staged;
+	cudaStream_t side[3] = {nullptr, nullptr, nullptr};     /* traceback launches of different kernel shapes run side by side */
 	int64_t opt_chunk = 0;
 	int64_t opt_small_chunk = 0;        /* "small_chunk" option (measurements): chunk length of launches too small to fill the device */
 	ssw_engine_timing timing;
@@ -246,6 +247,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out, &e->d_sync};
 	for (SswDevBuf* b : bufs) b->release();
 	e->staged.release();
+	for (cudaStream_t& st : e->side) if (st) { cudaStreamDestroy(st); st = nullptr; }
 	if (e->stream) cudaStreamDestroy(e->stream);
 	delete e;
 }
@@ -1295,7 +1297,7 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 	phase.lap("general: records");
 	/* ---- P3 ---- */
 	if (!tb.empty()) {
-		rc = ssw_traceback_run(e->stream, tb, e->d_q.as<int8_t>(), e->d_r.as<int8_t>(), e->d_mat.as<int8_t>(), P.n,
+		rc = ssw_traceback_run(e->stream, e->side, tb, e->d_q.as<int8_t>(), e->d_r.as<int8_t>(), e->d_mat.as<int8_t>(), P.n,
 		                       P.gap_open, P.gap_extend, &e->d_tb, &e->timing.traceback_ms, &e->timing.other_launches,
 		                       [&](size_t i, const uint32_t* words, int32_t len, int failed) -> int {
 			ssw_batch_result& r = results[tb_pair[i]];

@@ -4,6 +4,7 @@
 
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -12,7 +13,7 @@
 
 /* counts device allocations and frees made through SswDevBuf: the engine re-reads the free device memory only when
  * this changed (cudaMemGetInfo costs milliseconds while a monitoring tool polls the driver) */
-inline unsigned long long& ssw_alloc_epoch() { static unsigned long long n = 1; return n; }
+inline std::atomic<unsigned long long>& ssw_alloc_epoch() { static std::atomic<unsigned long long> n{1}; return n; }
 
 /* grow-only device buffer */
 struct SswDevBuf {
@@ -56,16 +57,19 @@ inline int ssw_ensure_dyn_smem(const void* fn, size_t smem)
 /* free memory of the current device, re-read only after one of our buffers was (re)allocated */
 inline size_t ssw_free_device_bytes()
 {
+	static std::mutex mu;
 	static size_t cache[64];
 	static unsigned long long epoch[64];
 	int dev = 0;
 	cudaGetDevice(&dev);
 	dev &= 63;
-	if (epoch[dev] != ssw_alloc_epoch()) {
+	std::lock_guard<std::mutex> lock(mu);
+	const unsigned long long now = ssw_alloc_epoch().load();
+	if (epoch[dev] != now) {
 		size_t free_b = 0, total_b = 0;
 		cudaMemGetInfo(&free_b, &total_b);
 		cache[dev] = free_b;
-		epoch[dev] = ssw_alloc_epoch();
+		epoch[dev] = now;
 	}
 	return cache[dev];
 }

@@ -494,12 +494,12 @@ ssw_cigar_pack_kernel(const SswTbTask* __restrict__ tasks, int n_tasks, const ui
 	for (int k = (int)threadIdx.x; k < len; k += (int)blockDim.x) dst[k] = src[k];
 }
 
-static int ssw_traceback_run(cudaStream_t stream, std::vector<SswTbTask>& tasks,
+static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side streams of the caller, created on demand */,
+                             std::vector<SswTbTask>& tasks,
                              const int8_t* d_q, const int8_t* d_r, const int8_t* d_mat, int n, int gapO, int gapE,
                              SswDevBuf* scratch, float* ms_acc, int64_t* launches,
                              const std::function<int(size_t, const uint32_t*, int32_t, int)>& emit)
 {
-	static cudaStream_t side[3] = {nullptr, nullptr, nullptr};
 	std::vector<size_t> active(tasks.size());
 	for (size_t i = 0; i < tasks.size(); ++i) {
 		SswTbTask& t = tasks[i];
