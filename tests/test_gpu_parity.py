@@ -439,3 +439,35 @@ def test_large_result_array_staged_copy(engine, checker, capfd):
         got = {k: int(res[p][k]) for k in FIELDS8}
         got["cigar"] = []
         assert C.diff_results(got, exp) == [], p
+
+
+def test_two_engines_in_two_threads(capfd):
+    """Independent engines (own stream, own scratch) used from two host threads at the same time give the results of a
+    lone engine -- the way a caller drives several batches (or several GPUs) from one process."""
+    from concurrent.futures import ThreadPoolExecutor
+    L = _pkg()
+    mat = C.dna_matrix(2, 2)
+    work = []
+    for seed in (1, 2):
+        ref, reads = C.make_dna_workload(200_000, 64, 150, seed_ref=100 + seed, seed_reads=200 + seed)
+        long_ref, long_reads = C.make_dna_workload(30_000, 3, 2500, seed_ref=300 + seed, seed_reads=400 + seed, decoy_frac=0.0, p_sub=0.05, p_ins=0.02, p_del=0.02)
+        work.append((reads, ref, long_reads, long_ref))
+
+    def run(w):
+        reads, ref, long_reads, long_ref = w
+        eng = L.BatchAligner(device=0)
+        out = []
+        for _ in range(2):
+            eng.set_sequences(reads, [ref])
+            out.append(eng.align(mat, 5, 3, 1, flag=0x0f, filters=0, filterd=32767, mask_len=75, score_size=2))
+            eng.set_sequences(long_reads, [long_ref])
+            out.append(eng.align(mat, 5, 3, 1, flag=2, filters=0, filterd=32767, mask_len=1000, score_size=2))
+        eng.close()
+        return out
+
+    solo = [run(w) for w in work]
+    with ThreadPoolExecutor(2) as ex:
+        both = list(ex.map(run, work))
+    for a, b in zip(solo, both):
+        for (ra, pa), (rb, pb) in zip(a, b):
+            assert (ra == rb).all() and (pa == pb).all()
