@@ -19,9 +19,12 @@ inline std::atomic<unsigned long long>& ssw_alloc_epoch() { static std::atomic<u
 struct SswDevBuf {
 	void* p = nullptr;
 	size_t cap = 0;
+	bool borrowed = false;          /* a view of another engine's buffer: never freed or grown here */
+	void borrow(const SswDevBuf& o) { if (!borrowed && p) { ++ssw_alloc_epoch(); cudaFree(p); } p = o.p; cap = o.cap; borrowed = true; }
 	int ensure(size_t bytes)
 	{
 		if (bytes <= cap) return 0;
+		if (borrowed) { fprintf(stderr, "[libssw-b200] internal: a borrowed buffer cannot grow\n"); return -1; }
 		++ssw_alloc_epoch();
 		if (p) cudaFree(p);
 		p = nullptr; cap = 0;
@@ -33,7 +36,7 @@ struct SswDevBuf {
 		cap = want;
 		return 0;
 	}
-	void release() { ++ssw_alloc_epoch(); if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() { if (!borrowed) { ++ssw_alloc_epoch(); if (p) cudaFree(p); } p = nullptr; cap = 0; borrowed = false; }
 	template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 

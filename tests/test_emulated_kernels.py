@@ -134,6 +134,18 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
                 got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
                 assert C.diff_results(got, exp) == [], (flag, k)
                 k += 1
+    # the same batch cut into slices that run on helper engines (views of the resident sequences, own scratch)
+    base_res, base_pool = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=100, score_size=2)
+    for slices in (2, 3):
+        eng.set_option("slices", slices)
+        res, pool = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=100, score_size=2)
+        assert len(pool) == len(base_pool)
+        for a, b in zip(res, base_res):
+            for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag", "cigar_len"):
+                assert int(a[f]) == int(b[f]), (slices, f)
+            if a["cigar_len"] > 0:
+                assert list(pool[a["cigar_off"]: a["cigar_off"] + a["cigar_len"]]) == list(base_pool[b["cigar_off"]: b["cigar_off"] + b["cigar_len"]])
+    eng.set_option("slices", 0)
     eng.set_option("super", 0)
     eng.close()
 
