@@ -8,6 +8,7 @@
  *   encoded_ops                  <- src/ssw.c:127-160
  *   ssw_align_batch              new: many pairs per call (include/ssw_batch.h)
  */
+#include <memory>
 #include <mutex>
 #include <vector>
 #include <string.h>
@@ -121,11 +122,12 @@ int collect_batch(ssw_engine* e, const ssw_batch_params* params, int32_t n_queri
 			cap += ql + span + 4;
 		}
 	}
-	std::vector<uint32_t> pool((size_t)cap + 8);
+	/* worst-case sized and mostly untouched: uninitialised storage, not a zero-filled vector */
+	std::unique_ptr<uint32_t[]> pool(new uint32_t[(size_t)cap + 8]);
 	int64_t used = 0;
-	const int rc = ssw_engine_align(e, params, n_pairs, pair_query, pair_ref, res.data(), pool.data(), (int64_t)pool.size(), &used);
+	const int rc = ssw_engine_align(e, params, n_pairs, pair_query, pair_ref, res.data(), pool.get(), cap + 8, &used);
 	if (rc) return rc;
-	for (int64_t p = 0; p < n_pairs; ++p) out[p] = record_from(res[p], pool.data());
+	for (int64_t p = 0; p < n_pairs; ++p) out[p] = record_from(res[p], pool.get());
 	return 0;
 }
 }  // namespace

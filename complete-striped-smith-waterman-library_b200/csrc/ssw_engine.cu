@@ -30,6 +30,7 @@
 #include "../../include/ssw_batch.h"
 
 #include <chrono>
+#include <memory>
 #include <thread>
 namespace {
 
@@ -1373,7 +1374,8 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 				for (int64_t p = 0; p < n_pairs; ++p) { pq_all[p] = (int32_t)(p / e->n_r); pr_all[p] = (int32_t)(p % e->n_r); }
 				pair_query = pq_all.data(); pair_ref = pr_all.data();
 			}
-			struct Slice { int64_t lo, hi, used; int rc; std::vector<uint32_t> pool; };
+			/* pool: worst-case sized, most of it never touched -- uninitialised storage, not a zero-filled vector */
+			struct Slice { int64_t lo, hi, used, cap; int rc; std::unique_ptr<uint32_t[]> pool; };
 			std::vector<Slice> sl((size_t)slices);
 			for (int k = 0; k < slices; ++k) {
 				Slice& s = sl[k];
@@ -1385,7 +1387,8 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 					const int64_t ql = e->q_off[q + 1] - e->q_off[q];
 					cap += ql + std::min<int64_t>(e->r_len[r], ql + ql * 127 / std::max<int>(P.gap_extend, 1)) + 4;
 				}
-				s.pool.resize((size_t)cap + 8);
+				s.cap = cap + 8;
+				s.pool.reset(new uint32_t[(size_t)s.cap]);
 				ssw_engine*& kid = e->kids[k];
 				if (!kid) { kid = ssw_engine_create(e->device); if (!kid) return -1; kid->is_kid = true; }
 				kid->n_q = e->n_q; kid->n_r = e->n_r; kid->q_off = e->q_off; kid->r_off = e->r_off; kid->r_len = e->r_len;
@@ -1396,7 +1399,7 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 			auto work = [&](int k) {
 				Slice& s = sl[k];
 				s.rc = ssw_engine_align(e->kids[k], params, s.hi - s.lo, pair_query + s.lo, pair_ref + s.lo, results + s.lo,
-				                        s.pool.data(), (int64_t)s.pool.size(), &s.used);
+				                        s.pool.get(), s.cap, &s.used);
 			};
 #ifdef SSW_CPU_EMU
 			for (int k = 0; k < slices; ++k) work(k);               /* the emulator's fibers are not thread-safe */
@@ -1414,7 +1417,7 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 				if (s.rc) return s.rc;
 				if (s.used > 0) {
 					if (!cigar_pool || *pool_used + s.used > pool_cap) { fprintf(stderr, "[libssw-b200] CIGAR pool too small\n"); return -1; }
-					memcpy(cigar_pool + *pool_used, s.pool.data(), sizeof(uint32_t) * (size_t)s.used);
+					memcpy(cigar_pool + *pool_used, s.pool.get(), sizeof(uint32_t) * (size_t)s.used);
 					for (int64_t p = s.lo; p < s.hi; ++p) if (results[p].cigar_off >= 0) results[p].cigar_off += (int32_t)*pool_used;
 					*pool_used += s.used;
 				}

@@ -15,6 +15,11 @@
 #ifndef SSW_CUDA_EMU_H
 #define SSW_CUDA_EMU_H
 
+#include <memory>
+#include <thread>
+#include <atomic>
+#include <map>
+#include <mutex>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
