@@ -317,3 +317,33 @@ def test_emulated_text_sequences(oracle, capfd):
     with pytest.raises(RuntimeError):
         eng.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=15, score_size=2)
     eng.close()
+
+
+def test_emulated_align_batch_c_entry(oracle, capfd):
+    """ssw_align_batch (host buffers in, heap s_align records out) on the emulator build."""
+    import ctypes as ct
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    lib = eng.lib
+    rng = np.random.default_rng(3)
+    ref = rng.integers(0, 4, size=400, dtype=np.int8)
+    reads = [C.mutate_read(rng, ref, int(rng.integers(0, 300)), 60, 0.05, 0.02, 0.02) for _ in range(5)]
+    qc, qo = L.concat(reads)
+    rc, ro = L.concat([ref])
+    mat = np.ascontiguousarray(C.dna_matrix(2, 2), dtype=np.int8)
+    P = L.BatchParams(mat.ctypes.data_as(ct.POINTER(ct.c_int8)), 5, 3, 1, 2, 0, 0, 30, 2)
+    out = (ct.c_void_p * len(reads))()
+    lib.ssw_align_batch.argtypes = [ct.c_void_p, ct.POINTER(L.BatchParams), ct.c_int32, ct.POINTER(ct.c_int8), ct.POINTER(ct.c_int64),
+                                    ct.c_int32, ct.POINTER(ct.c_int8), ct.POINTER(ct.c_int64), ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p]
+    lib.ssw_align_batch.restype = ct.c_int
+    lib.align_destroy.argtypes = [ct.c_void_p]
+    assert lib.ssw_align_batch(eng.h, ct.byref(P), len(reads), qc.ctypes.data_as(ct.POINTER(ct.c_int8)), qo.ctypes.data_as(ct.POINTER(ct.c_int64)),
+                               1, rc.ctypes.data_as(ct.POINTER(ct.c_int8)), ro.ctypes.data_as(ct.POINTER(ct.c_int64)), len(reads), None, None, out) == 0
+    for i, q in enumerate(reads):
+        a = ct.cast(out[i], ct.POINTER(C.SAlign)).contents
+        exp = oracle.align(q, ref, mat, 5, 3, 1, 2, 0, 0, 30, 2)
+        assert (a.score1, a.ref_begin1, a.ref_end1, a.read_begin1, a.read_end1) == (exp["score1"], exp["ref_begin1"], exp["ref_end1"], exp["read_begin1"], exp["read_end1"])
+        assert [int(a.cigar[k]) for k in range(a.cigarLen)] == exp["cigar"]
+        lib.align_destroy(out[i])
+    eng.close()
