@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 import common as C
@@ -62,3 +63,34 @@ def test_library_exports_the_cpp_wrapper():
                    "Aligner::Align(char const*, char const*,", "Aligner::Align(char const*, unsigned long, StripedSmithWaterman::Filter const&",
                    "Aligner::Align(char const*, StripedSmithWaterman::Filter const&"):
         assert "StripedSmithWaterman::" + member in out, member
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not os.path.exists(C.LIB_OURS), reason="libssw.so not built yet")
+@pytest.mark.skipif(_have_gpu(), reason="needs a host without a GPU")
+def test_no_cpu_fallback_without_a_gpu(capfd, tmp_path):
+    """Without a CUDA device the product refuses to work, loudly: no engine, ssw_align -> NULL, the CLI exits non-zero."""
+    lib = ct.CDLL(C.LIB_OURS)
+    lib.ssw_engine_create.restype = ct.c_void_p
+    assert not lib.ssw_engine_create(-1)
+    assert "no CPU compute path" in capfd.readouterr().err
+    ours = C.load_ours()
+    q = np.array([0, 1, 2, 3] * 10, dtype=np.int8)
+    r = np.array([0, 1, 2, 3] * 30, dtype=np.int8)
+    assert ours.align(q, r, C.dna_matrix(2, 2), 5, 3, 1, 0, 0, 0, 15, 2) is None
+    cli = os.path.join(C.PKG, "ssw_batch_cli")
+    if os.path.exists(cli):
+        import json
+        with open(os.path.join(C.GOLDEN, "consumer_outputs.json")) as f:
+            files = json.load(f)["files"]
+        (tmp_path / "r1.fa").write_text(files["r1.fa"])
+        (tmp_path / "q.fq").write_text(files["r1_query.fq"])
+        out = subprocess.run([cli, "r1.fa", "q.fq"], capture_output=True, text=True, cwd=str(tmp_path))
+        assert out.returncode != 0 and out.stdout == ""
