@@ -359,7 +359,7 @@ def main():
                              "note": "integer-issue bound recurrence (150 cells per reference byte): the HBM fraction is reported as required, "
                                      "the meaningful efficiency is alu_roofline"},
                 "alu_roofline": alu_roofline(cells_rank, fill_s)}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:            # reported baseline, rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             sample = args.cpu_sample or 4 * cores
             if not C.have_ref():
