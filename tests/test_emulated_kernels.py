@@ -7,6 +7,7 @@ import importlib.util
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -347,3 +348,22 @@ def test_emulated_align_batch_c_entry(oracle, capfd):
         assert [int(a.cigar[k]) for k in range(a.cigarLen)] == exp["cigar"]
         lib.align_destroy(out[i])
     eng.close()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/pyssw.py"), reason="reference tree not present (build container only)")
+def test_reference_python_driver_unmodified(tmp_path):
+    """The reference's own pyssw.py + ssw_lib.py (ctypes) load a library by the name libssw.so: given the emulator build
+    of our sources they print what they print with the reference's ssw.c (the ctypes struct mirrors stay compatible)."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    if not C.have_ref():
+        pytest.skip("compiled reference not available")
+    outs = []
+    for name, lib in (("ours", os.path.join(EMU_DIR, "libssw_emu.so")), ("ref", C.LIB_REF)):
+        d = tmp_path / name
+        d.mkdir()
+        os.symlink(lib, d / "libssw.so")
+        r = subprocess.run([sys.executable, "/root/reference/src/pyssw.py", "-l", str(d), "-c", "/root/reference/demo/r1.fa",
+                            "/root/reference/demo/r1_query.fq"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append("\n".join(l for l in r.stdout.splitlines() if not l.startswith("CPU time")))
+    assert outs[0] == outs[1] and "optimal_alignment_score: 52" in outs[0]
