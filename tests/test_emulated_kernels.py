@@ -367,3 +367,31 @@ def test_reference_python_driver_unmodified(tmp_path):
         assert r.returncode == 0, r.stderr[-500:]
         outs.append("\n".join(l for l in r.stdout.splitlines() if not l.startswith("CPU time")))
     assert outs[0] == outs[1] and "optimal_alignment_score: 52" in outs[0]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/main.c"), reason="reference tree not present (build container only)")
+def test_reference_c_consumers_unmodified_on_emulator_build(tmp_path):
+    """CPU replica of test_gpu_parity.py::test_unmodified_reference_consumers_on_our_library: the reference's ssw_test,
+    example_c and example_cpp, compiled unmodified against the emulator build of our sources, reproduce the frozen outputs."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    ref = "/root/reference/src"
+    link = ["-L" + EMU_DIR, "-l:libssw_emu.so", "-Wl,-rpath," + EMU_DIR, "-lm", "-lz"]
+    exe = {}
+    for name, cmd in (("ssw_test", ["gcc", "-O2", "-o", str(tmp_path / "ssw_test"), ref + "/main.c"] + link),
+                      ("example_c", ["gcc", "-O2", "-o", str(tmp_path / "example_c"), ref + "/example.c"] + link),
+                      ("example_cpp", ["g++", "-O2", "-o", str(tmp_path / "example_cpp"), ref + "/example.cpp", ref + "/ssw_cpp.cpp"] + link)):
+        subprocess.run(cmd, check=True)
+        exe[name] = str(tmp_path / name)
+    with open(os.path.join(C.GOLDEN, "consumer_outputs.json")) as f:
+        G = json.load(f)
+    for name, text in G["files"].items():
+        (tmp_path / name).write_text(text)
+    n = 0
+    for run in G["runs"]:
+        if "1k.fa" in run["args"]:
+            continue                       # 100 reads per run: minutes on the emulator; the GPU suite runs them
+        out = subprocess.run([exe[run["exe"]]] + run["args"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+        got = "\n".join(l for l in out.stdout.splitlines() if not l.startswith("CPU time"))
+        assert got == run["stdout"], (run["exe"], run["args"])
+        n += 1
+    assert n >= 8
