@@ -63,7 +63,7 @@ static int64_t g_latency_cols = 1 << 20;   /* "latency_cols" option: passes over
 static int g_force_inst = -1;      /* "inst" option (measurements): use this forward instance whenever it covers the query */
 static int pick_inst(int lp)
 {
-	if (g_force_inst >= 0 && g_force_inst < kNumFwd && kInst[g_force_inst].G * kInst[g_force_inst].R >= lp) return g_force_inst;
+	if (g_force_inst >= 0 && g_force_inst < kNumInst && kInst[g_force_inst].G * kInst[g_force_inst].R >= lp) return g_force_inst;   /* 10..13: the 32-lane layouts */
 	for (int i = 0; i < kNumFwd; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
 	return -1;
 }
@@ -1129,6 +1129,10 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 			case 7: rc = launch_fill<16, 20>(e, (int)n_items, +1, 1, P); break;
 			case 8: rc = launch_fill<32, 16>(e, (int)n_items, +1, 1, P); break;
 			case 9: rc = launch_fill<32, 20>(e, (int)n_items, +1, 1, P); break;
+			case 10: rc = launch_fill<32, 4>(e, (int)n_items, +1, 1, P); break;     /* 10..13: only through the "inst" option */
+			case 11: rc = launch_fill<32, 5>(e, (int)n_items, +1, 1, P); break;
+			case 12: rc = launch_fill<32, 8>(e, (int)n_items, +1, 1, P); break;
+			case 13: rc = launch_fill<32, 10>(e, (int)n_items, +1, 1, P); break;
 			default: break;
 			}
 			if (rc) return rc < 0 ? rc : -1;
