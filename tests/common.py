@@ -265,3 +265,157 @@ def diff_results(a, b, fields=FIELDS):
     if a is None or b is None:
         return [] if a is b else [("null", a, b)]
     return [(f, a[f], b[f]) for f in fields if a[f] != b[f]]
+
+
+# --------------------------------------------------------------------------
+# the BASELINE.json configurations as (queries, refs, params) -- shared by the parity tests and bench.py
+# --------------------------------------------------------------------------
+
+def config_workload(cfg, n_reads=None, n_queries=None, n_targets=None, ref_len=None, read_len=None):
+    """SURVEY 8(d) workloads.  Returns dict(queries, refs, mat, n, gapO, gapE, flag, filters, filterd, mask_len, score_size, name).
+    cfg 2: 1,000 x 150 bp vs 5 Mbp (seeds 1001/2002);  cfg 3: 100,000 x 150 bp vs the same reference (seed 3003);
+    cfg 4: protein grid, 300 aa queries (seed 4004) x 400 aa targets (seed 4005, every 10th target embeds a mutated
+    query segment), BLOSUM50, word scores;  cfg 5: 1,000 x 10 kbp vs 100 kbp (seeds 5005/5006), flag 2 (CIGAR)."""
+    if cfg in (2, 3):
+        n = n_reads or (1000 if cfg == 2 else 100_000)
+        ref, reads = make_dna_workload(ref_len or 5_000_000, n, read_len or 150, seed_ref=1001, seed_reads=2002 if cfg == 2 else 3003)
+        return dict(queries=reads, refs=[ref], mat=dna_matrix(2, 2), n=5, gapO=3, gapE=1, flag=0, filters=0, filterd=0,
+                    mask_len=(read_len or 150) // 2, score_size=2, name="config%d" % cfg)
+    if cfg == 4:
+        nq, nt = n_queries or 10_000, n_targets or 50_000
+        rq, rt = np.random.default_rng(4004), np.random.default_rng(4005)
+        queries = [rq.integers(0, 20, size=300).astype(np.int8) for _ in range(nq)]
+        targets = []
+        for t in range(nt):
+            s = rt.integers(0, 20, size=400).astype(np.int8)
+            if t % 10 == 0:
+                q = queries[int(rt.integers(0, len(queries)))]
+                a = int(rt.integers(0, 100))
+                seg = q[a: a + 200].copy()
+                m = rt.random(len(seg)) < 0.2
+                seg[m] = rt.integers(0, 20, size=int(m.sum()))
+                b = int(rt.integers(0, 200))
+                s[b: b + 200] = seg
+            targets.append(s)
+        return dict(queries=queries, refs=targets, mat=BLOSUM50, n=24, gapO=3, gapE=1, flag=0, filters=0, filterd=0,
+                    mask_len=150, score_size=1, name="config4")
+    if cfg == 5:
+        n = n_reads or 1000
+        ref, reads = make_dna_workload(ref_len or 100_000, n, read_len or 10_000, seed_ref=5005, seed_reads=5006, decoy_frac=0.0, p_sub=0.05, p_ins=0.02, p_del=0.02)
+        return dict(queries=reads, refs=[ref], mat=dna_matrix(2, 2), n=5, gapO=3, gapE=1, flag=2, filters=0, filterd=32767,
+                    mask_len=(read_len or 10_000) // 2, score_size=2, name="config5")
+    raise ValueError(cfg)
+
+
+# --------------------------------------------------------------------------
+# many pairs on all host cores through a CPU implementation (oracle/ssw_harness.c; test infrastructure)
+# --------------------------------------------------------------------------
+
+LIB_HARNESS = os.path.join(ORACLE_DIR, "libssw_harness.so")
+
+HARNESS_DTYPE = np.dtype([("score1", "<u2"), ("score2", "<u2"), ("ref_begin1", "<i4"), ("ref_end1", "<i4"),
+                          ("read_begin1", "<i4"), ("read_end1", "<i4"), ("ref_end2", "<i4"),
+                          ("cigar_off", "<i4"), ("cigar_len", "<i4"), ("flag", "<u2"), ("status", "<u2")])
+assert HARNESS_DTYPE.itemsize == 36
+
+
+def effective_cores():
+    """Host cores this process may really use: scheduler affinity capped by the cgroup CPU quota (a 1-GPU lease of a
+    big node reports all of the node's CPUs through os.cpu_count())."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    info = {"affinity": n, "cpu_count": os.cpu_count() or 1, "cgroup_quota": None}
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                      # cgroup v2
+            a, b = f.read().split()[:2]
+            if a != "max":
+                quota = float(a) / float(b)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:      # cgroup v1
+                q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                p = float(f.read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota is not None:
+        info["cgroup_quota"] = quota
+        n = max(1, min(n, int(np.ceil(quota))))
+    info["effective"] = n
+    return n, info
+
+
+def _concat(seqs):
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs])
+    cat = np.concatenate([np.asarray(s, dtype=np.int8) for s in seqs]) if len(seqs) else np.zeros(0, np.int8)
+    return np.ascontiguousarray(cat, dtype=np.int8), off
+
+
+def cpu_batch(queries, refs, pair_q, pair_r, mat, n, gapO=3, gapE=1, flag=0, filters=0, filterd=0, mask_len=-1,
+              score_size=2, threads=None, want_cigar=None, impl=None):
+    """Align pairs (pair_q[i], pair_r[i]) with a CPU implementation on `threads` host threads (pthread harness).
+    impl: "reference" (oracle/_ref/libssw_ref.so), "port" (scalar oracle) or None = reference if present.
+    Returns (records[HARNESS_DTYPE], pool[uint32], seconds, cells, kind)."""
+    build_oracle()
+    if impl is None:
+        impl = "reference" if have_ref() else "port"
+    path, prefix = (LIB_REF, b"") if impl == "reference" else (LIB_ORACLE, b"oracle_")
+    H = ct.CDLL(LIB_HARNESS)
+    f = H.ssw_harness_run
+    f.restype = ct.c_int
+    f.argtypes = [ct.c_char_p, ct.c_char_p, ct.c_int32, ct.c_int64, I8P, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int32),
+                  I8P, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int32), I8P, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32,
+                  ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_void_p, ct.POINTER(ct.c_uint32), ct.c_int64,
+                  ct.POINTER(ct.c_int64), ct.POINTER(ct.c_double), ct.POINTER(ct.c_int64)]
+    qc, qo = _concat(queries)
+    rc, ro = _concat(refs)
+    pq = np.ascontiguousarray(pair_q, dtype=np.int32)
+    pr = np.ascontiguousarray(pair_r, dtype=np.int32)
+    m = np.ascontiguousarray(mat, dtype=np.int8)
+    out = np.zeros(len(pq), dtype=HARNESS_DTYPE)
+    if want_cigar is None:
+        want_cigar = bool(flag & 7)
+    cap = 1
+    if want_cigar:
+        ql, rl = np.diff(qo), np.diff(ro)
+        cap = int(np.sum(ql[pq] + np.minimum(rl[pr], ql[pq] * 128) + 4))
+    pool = np.zeros(cap, dtype=np.uint32)
+    used, secs, cells = ct.c_int64(0), ct.c_double(0), ct.c_int64(0)
+    if threads is None:
+        threads = effective_cores()[0]
+    rv = f(path.encode(), prefix, int(threads), len(pq), i8ptr(qc), qo.ctypes.data_as(ct.POINTER(ct.c_int64)),
+           pq.ctypes.data_as(ct.POINTER(ct.c_int32)), i8ptr(rc), ro.ctypes.data_as(ct.POINTER(ct.c_int64)),
+           pr.ctypes.data_as(ct.POINTER(ct.c_int32)), i8ptr(m), n, gapO, gapE, flag, filters, filterd, mask_len, score_size,
+           out.ctypes.data_as(ct.c_void_p), pool.ctypes.data_as(ct.POINTER(ct.c_uint32)) if want_cigar else None, cap,
+           ct.byref(used), ct.byref(secs), ct.byref(cells))
+    if rv:
+        raise RuntimeError("ssw_harness_run failed (%d)" % rv)
+    return out, pool[: used.value], secs.value, cells.value, impl
+
+
+CMP_FIELDS = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag", "status")
+
+
+def compare_records(got, got_pool, exp, exp_pool, idx=None):
+    """Field-by-field comparison of batch records (ssw_batch_result layout) incl. every CIGAR word.
+    got[idx[i]] is compared with exp[i].  Returns the list of mismatching positions i."""
+    bad = []
+    for i in range(len(exp)):
+        g = got[idx[i]] if idx is not None else got[i]
+        e = exp[i]
+        if any(int(g[f]) != int(e[f]) for f in CMP_FIELDS) or int(g["cigar_len"]) != int(e["cigar_len"]):
+            bad.append(i)
+            continue
+        if int(e["cigar_len"]) > 0 and int(e["cigar_off"]) >= 0:
+            gw = got_pool[int(g["cigar_off"]): int(g["cigar_off"]) + int(g["cigar_len"])]
+            ew = exp_pool[int(e["cigar_off"]): int(e["cigar_off"]) + int(e["cigar_len"])]
+            if len(gw) != len(ew) or not np.array_equal(np.asarray(gw), np.asarray(ew)):
+                bad.append(i)
+    return bad

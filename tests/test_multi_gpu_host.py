@@ -1,6 +1,7 @@
-"""CPU test of the N>1 host logic (world_size 2, gloo): cell-balanced sharding of the pair list and the gather of
-result records to rank 0.  The per-rank alignment itself is stood in for by the oracle (test infrastructure);
-on the GPU box the same code path runs with backend nccl inside bench.py."""
+"""CPU tests of the N>1 host logic (world_size 2, gloo): cell-balanced sharding of the pair list and the gather of
+result records (and, two-phase, of the variable-length CIGAR words) to rank 0.  In the first test the per-rank
+alignment is stood in for by the oracle; in the second every rank runs the PRODUCT's engine and kernel sources
+(emulator build, tests/cuda_emu) on its shard, as bench.py does with backend nccl on the GPU box."""
 import importlib.util
 import os
 import socket
@@ -73,5 +74,58 @@ def test_gather_to_rank0_world2_gloo():
         p.start()
     for p in procs:
         p.join(timeout=240)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
+
+
+def _worker_emu(rank, world, port, q):
+    """every rank: product engine (emulator build) on its cell-balanced shard, flag 2 (CIGARs) -> gather_batch"""
+    import subprocess
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(C.ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    D = _mod("ssw_dist")
+    L = _mod("ssw_lib")
+    emu_dir = os.path.join(C.ROOT, "tests", "cuda_emu")
+    ref, reads = C.make_dna_workload(2500, 11, 70, seed_ref=15, seed_reads=16, p_ins=0.03, p_del=0.03)
+    reads[2] = reads[2][:31]
+    reads[7] = np.random.default_rng(3).integers(0, 4, size=70, dtype=np.int8)       # decoy: tiny or no CIGAR
+    mat = C.dna_matrix(2, 2)
+    cells = [len(x) * len(ref) for x in reads]
+    lo, hi = D.shard_range(cells, rank, world)
+    eng = L.BatchAligner(lib_dir=emu_dir, lib_name="libssw_emu.so")
+    eng.set_sequences(reads[lo:hi], [ref])
+    res, pool = eng.align(mat, 5, 3, 1, flag=2, filters=0, filterd=32767, mask_len=35, score_size=2)
+    eng.close()
+    recs, words = D.gather_batch(res, pool, rank, world)
+    ok = None
+    if rank == 0:
+        exp, exp_pool, _, _, _ = C.cpu_batch(reads, [ref], np.arange(len(reads)), np.zeros(len(reads)), mat, 5, 3, 1, flag=2,
+                                            filters=0, filterd=32767, mask_len=35, score_size=2, impl="port", threads=2)
+        ok = len(recs) == len(reads) and C.compare_records(recs, words, exp, exp_pool) == [] and int((recs["cigar_len"] > 0).sum()) >= 8
+        q.put(bool(ok))
+    else:
+        assert recs is None and words is None
+    dist.destroy_process_group()
+
+
+def test_product_engine_per_rank_with_cigar_gather_world2_gloo():
+    import subprocess
+    import torch.multiprocessing as mp
+    subprocess.run(["make", "-s", "-C", os.path.join(C.ROOT, "tests", "cuda_emu")], check=True)
+    C.build_oracle()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_emu, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=400)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True

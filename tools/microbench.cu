@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #define ITERS 2048
 #define ILP 8
@@ -105,6 +106,128 @@ __global__ void probe_mix_h(uint32_t* out, long long* cyc, uint32_t seed)
 	if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+
+// ---- second-pipe probes (round 2): can packed-half adds on the FMA pipe run beside DPX maxima on the ALU pipe? ----
+// Independent chains only (no cross-chain dependencies), so the figures are issue rates, not latencies.
+__device__ __forceinline__ uint32_t hfma2_relu(uint32_t a, uint32_t one, uint32_t c)
+{
+	uint32_t d; asm volatile("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t one, uint32_t c)
+{
+	uint32_t d; asm volatile("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t c)
+{
+	uint32_t d; asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(c)); return d;
+}
+
+// NA ALU-pipe ops (VIMNMX.S16x2 when AOP == 0, VIADDMNMX.S16x2 when AOP == 1) and NB FMA-pipe ops
+// (HFMA2.RELU when FOP == 0, HADD2 when FOP == 1, HFMA2 when FOP == 2, IMAD when FOP == 3) per inner step, every chain independent
+template <int NA, int NB, int AOP, int FOP>
+__global__ void probe_pipes(uint32_t* out, long long* cyc, uint32_t seed)
+{
+	uint32_t va[12], vb[12];
+#pragma unroll
+	for (int i = 0; i < 12; ++i) { va[i] = seed * (i + 1) + threadIdx.x; vb[i] = 0x3c003c00u + ((seed * (i + 9) + threadIdx.x) & 0x00ff00ffu); }
+	const uint32_t one = 0x3c003c00u;                    // 1.0 | 1.0
+	uint32_t b = (seed & 0x00030003u) | 0x00010001u, c = 0xbc00bc00u;      // c = -1.0 | -1.0
+	asm volatile("" : "+r"(b), "+r"(c));
+	__syncthreads();
+	long long t0 = clock64();
+#pragma unroll 1
+	for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+#pragma unroll
+			for (int i = 0; i < (NA > NB ? NA : NB); ++i) {
+				if (i < NA) va[i] = AOP == 0 ? __vmaxs2(va[i], b) + 0 : __viaddmax_s16x2(va[i], b, c);
+				if (i < NB) vb[i] = FOP == 0 ? hfma2_relu(vb[i], one, c) : FOP == 1 ? hadd2(vb[i], c) : FOP == 2 ? hfma2(vb[i], one, c) : vb[i] * b + c;
+			}
+		}
+		if (AOP == 0) b ^= (uint32_t)it;                 // keep the maxima from being folded
+	}
+	long long t1 = clock64();
+	uint32_t acc = 0;
+#pragma unroll
+	for (int i = 0; i < 12; ++i) acc ^= va[i] ^ vb[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+	if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// The recurrence itself, R rows per lane, no memory traffic: scores rotate through registers.
+//   MODE 0: the shipped s16x2 formulation (5 ALU-pipe DPX ops per cell pair)
+//   MODE 1: packed-half formulation: 4 HFMA2.RELU (FMA pipe) + 4 VIMNMX.S16x2 (ALU pipe) per cell pair; all values >= 0 so the
+//           bit patterns order like integers
+//   MODE 2: hybrid: X and H as in MODE 0 (VIADDMNMX.RELU, VIMNMX), the E/F updates with HFMA2.RELU + VIMNMX -- needs values that are
+//           valid in both encodings, so it is an issue-rate probe only
+template <int R, int MODE>
+__global__ void probe_cells(uint32_t* out, long long* cyc, uint32_t seed)
+{
+	uint32_t Hd[R], E[R], s[R];
+#pragma unroll
+	for (int k = 0; k < R; ++k) {
+		Hd[k] = 0; E[k] = 0;
+		const int v = (int)((seed * (k + 3) + threadIdx.x * 7) % 5) - 2;
+		if (MODE == 0) s[k] = ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16);
+		else { const __half hv = __int2half_rn(v); const uint32_t hb = (uint32_t)__half_as_ushort(hv); s[k] = hb | (hb << 16); }
+	}
+	const uint32_t one = 0x3c003c00u;
+	uint32_t negO = MODE == 0 ? 0xfffdfffdu : 0xc200c200u;            // -3
+	uint32_t negE = MODE == 0 ? 0xffffffffu : 0xbc00bc00u;            // -1
+	asm volatile("" : "+r"(negO), "+r"(negE));
+	uint32_t F = 0, cm = 0, inH = 0;
+	__syncthreads();
+	long long t0 = clock64();
+#pragma unroll 1
+	for (int it = 0; it < ITERS; ++it) {
+		uint32_t Hn[R];
+		F = inH;
+#pragma unroll
+		for (int k = 0; k < R; ++k) {
+			if (MODE == 0) {
+				const uint32_t X = __viaddmax_s16x2_relu(Hd[k], s[k], E[k]);
+				const uint32_t Xg = __vadd2(X, negO);
+				E[k] = __viaddmax_s16x2(E[k], negE, Xg);
+				Hn[k] = __vmaxs2(X, F);
+				F = __viaddmax_s16x2(F, negE, Xg);
+			} else if (MODE == 1) {
+				const uint32_t t1 = hfma2_relu(Hd[k], one, s[k]);
+				const uint32_t X = __vmaxs2(t1, E[k]);
+				const uint32_t Xg = hfma2_relu(X, one, negO);
+				E[k] = __vmaxs2(hfma2_relu(E[k], one, negE), Xg);
+				Hn[k] = __vmaxs2(X, F);
+				F = __vmaxs2(hfma2_relu(F, one, negE), Xg);
+			} else {
+				const uint32_t X = __viaddmax_s16x2_relu(Hd[k], s[k], E[k]);
+				const uint32_t Xg = hfma2_relu(X, one, negO);
+				E[k] = __vmaxs2(hfma2_relu(E[k], one, negE), Xg);
+				Hn[k] = __vmaxs2(X, F);
+				F = __vmaxs2(hfma2_relu(F, one, negE), Xg);
+			}
+		}
+		uint32_t m = __vimax3_s16x2(Hn[0], Hn[1], Hn[2]);
+#pragma unroll
+		for (int k = 3; k + 1 < R; k += 2) m = __vimax3_s16x2(m, Hn[k], Hn[k + 1]);
+		cm = __vmaxs2(cm, m);
+		Hd[0] = inH;
+#pragma unroll
+		for (int k = 1; k < R; ++k) Hd[k] = Hn[k - 1];
+		inH = Hn[R - 1] ^ (uint32_t)(it & 1);
+		// rotate the scores so that nothing is loop-invariant
+		const uint32_t s0 = s[0];
+#pragma unroll
+		for (int k = 0; k + 1 < R; ++k) s[k] = s[k + 1];
+		s[R - 1] = s0;
+	}
+	long long t1 = clock64();
+	uint32_t acc = cm ^ F;
+#pragma unroll
+	for (int k = 0; k < R; ++k) acc ^= E[k] ^ Hd[k];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+	if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 template <class K>
 static double run(K kern, int threads, int ops_per_iter, int sms)
 {
@@ -159,6 +282,29 @@ int main()
 			printf(", \"mix_dpx_hmnmx2_1024thr\": {\"8+0\": %.3f, \"6+2\": %.3f, \"4+4\": %.3f, \"HMNMX2 alone\": %.3f}", h80, h62, h44, h08);
 			printf(", \"mix_dpx_imad_1024thr\": {\"4+4\": %.3f, \"6+2\": %.3f, \"8+0\": %.3f}", m44, m62, m80);
 			// fill kernel: 5.5 DPX ops per lane per two cells -> cells/clk/SM = rate * 32 lanes * 2 / 5.5
+
+			// round 2: second-pipe probes
+			printf(", \"pipes_1024thr\": {");
+			printf("\"HFMA2.RELU alone x8\": %.3f", run(probe_pipes<0, 8, 0, 0>, threads, 4 * 8, sms));
+			printf(", \"HADD2 alone x8\": %.3f", run(probe_pipes<0, 8, 0, 1>, threads, 4 * 8, sms));
+			printf(", \"HFMA2 alone x8\": %.3f", run(probe_pipes<0, 8, 0, 2>, threads, 4 * 8, sms));
+			printf(", \"IMAD alone x8\": %.3f", run(probe_pipes<0, 8, 0, 3>, threads, 4 * 8, sms));
+			printf(", \"VIMNMX alone x8\": %.3f", run(probe_pipes<8, 0, 0, 0>, threads, 4 * 8, sms));
+			printf(", \"VIADDMNMX alone x8\": %.3f", run(probe_pipes<8, 0, 1, 0>, threads, 4 * 8, sms));
+			printf(", \"VIMNMX 8 + HFMA2.RELU 8\": %.3f", run(probe_pipes<8, 8, 0, 0>, threads, 4 * 16, sms));
+			printf(", \"VIMNMX 9 + HFMA2.RELU 8\": %.3f", run(probe_pipes<9, 8, 0, 0>, threads, 4 * 17, sms));
+			printf(", \"VIMNMX 8 + HFMA2.RELU 4\": %.3f", run(probe_pipes<8, 4, 0, 0>, threads, 4 * 12, sms));
+			printf(", \"VIMNMX 8 + HADD2 8\": %.3f", run(probe_pipes<8, 8, 0, 1>, threads, 4 * 16, sms));
+			printf(", \"VIADDMNMX 8 + HFMA2.RELU 8\": %.3f", run(probe_pipes<8, 8, 1, 0>, threads, 4 * 16, sms));
+			printf(", \"VIADDMNMX 8 + IMAD 8\": %.3f", run(probe_pipes<8, 8, 1, 3>, threads, 4 * 16, sms));
+			printf(", \"VIMNMX 8 + IMAD 8\": %.3f", run(probe_pipes<8, 8, 0, 3>, threads, 4 * 16, sms));
+			printf("}");
+			// the recurrence itself: warp-steps (one column of R rows) per clock per SM -> cell updates per clock per SM = x * 32 * 2 * R
+			for (int thr = 256; thr <= 512; thr *= 2) {
+				const double c0 = run(probe_cells<20, 0>, thr, 1, sms), c1 = run(probe_cells<20, 1>, thr, 1, sms), c2 = run(probe_cells<20, 2>, thr, 1, sms);
+				const double k = 32.0 * 2.0 * 20.0 * sms * (clk_khz * 1e3) / 1e9;
+				printf(", \"cells_R20_%dthr_gcups\": {\"s16x2 (shipped)\": %.1f, \"f16x2: 4 HFMA2.RELU + 4 VIMNMX\": %.1f, \"hybrid\": %.1f}", thr, c0 * k, c1 * k, c2 * k);
+			}
 			const double cells_per_clk_sm = r[0] * 32.0 * 2.0 / 5.5;
 			printf(", \"gcups_peak_5p5_ops_per_cellpair\": %.1f", cells_per_clk_sm * sms * (clk_khz * 1e3) / 1e9);
 		}
