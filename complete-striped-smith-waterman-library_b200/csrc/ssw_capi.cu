@@ -8,12 +8,17 @@
  *   encoded_ops                  <- src/ssw.c:127-160
  *   ssw_align_batch              new: many pairs per call (include/ssw_batch.h)
  */
+#include <condition_variable>
+#include <exception>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <utility>
 #include <vector>
 #include <string.h>
 
 #include "ssw_common.cuh"
+#include "ssw_host.h"
 #include "../../include/ssw.h"
 #include "../../include/ssw_batch.h"
 
@@ -37,14 +42,65 @@ struct _profile {
 };
 
 namespace {
+/*
+ * The engines behind ssw_align / ssw_align_batch(NULL, ...).  The reference's ssw_align is re-entrant (no locks, no
+ * mutable globals: SURVEY 8(b) Threading), so concurrent callers must not be serialised on one engine: calls draw an
+ * engine (own stream, own scratch) from a small pool that grows on demand up to SSW_B200_ENGINES (default 8); a caller
+ * finding all of them busy waits for one.  A free engine that already holds the caller's reference is preferred
+ * (ssw_engine_set_pair skips the upload then).
+ */
+struct PoolEntry { ssw_engine* e; bool busy; const int8_t* last_ref; int32_t last_len; };
 std::mutex g_mu;
-ssw_engine* g_engine = nullptr;
+std::condition_variable g_cv;
+std::vector<PoolEntry> g_pool;
+std::vector<std::pair<std::string, int64_t>> g_pool_options;       /* ssw_engine_set_option(NULL, ...) calls, replayed on new engines */
 
-ssw_engine* default_engine()
+int pool_limit()
 {
-	if (!g_engine) g_engine = ssw_engine_create(-1);
-	return g_engine;
+	static int lim = 0;
+	if (!lim) { const char* v = getenv("SSW_B200_ENGINES"); lim = v && atoi(v) > 0 ? atoi(v) : 8; if (lim > 64) lim = 64; }
+	return lim;
 }
+
+ssw_engine* pool_acquire(const int8_t* ref, int32_t refLen)
+{
+	std::unique_lock<std::mutex> lock(g_mu);
+	for (;;) {
+		int pick = -1;
+		for (size_t i = 0; i < g_pool.size(); ++i) {
+			if (g_pool[i].busy) continue;
+			if (ref && g_pool[i].last_ref == ref && g_pool[i].last_len == refLen) { pick = (int)i; break; }
+			if (pick < 0) pick = (int)i;
+		}
+		if (pick >= 0) {
+			g_pool[pick].busy = true; g_pool[pick].last_ref = ref; g_pool[pick].last_len = refLen;
+			return g_pool[pick].e;
+		}
+		if ((int)g_pool.size() < pool_limit()) {
+			ssw_engine* e = ssw_engine_create(-1);
+			if (!e) return nullptr;
+			for (const auto& kv : g_pool_options) ssw_engine_set_option(e, kv.first.c_str(), kv.second);
+			g_pool.push_back(PoolEntry{e, true, ref, refLen});
+			return e;
+		}
+		g_cv.wait(lock);
+	}
+}
+
+void pool_release(ssw_engine* e)
+{
+	{
+		std::lock_guard<std::mutex> lock(g_mu);
+		for (PoolEntry& p : g_pool) if (p.e == e) p.busy = false;
+	}
+	g_cv.notify_one();
+}
+
+struct PoolGuard {
+	ssw_engine* e;
+	explicit PoolGuard(ssw_engine* x) : e(x) {}
+	~PoolGuard() { if (e) pool_release(e); }
+};
 
 s_align* record_from(const ssw_batch_result& r, const uint32_t* pool)
 {
@@ -62,6 +118,23 @@ s_align* record_from(const ssw_batch_result& r, const uint32_t* pool)
 	return a;
 }
 }  // namespace
+
+/* ssw_engine_set_option(NULL, name, value): every engine of the pool, present and future */
+int ssw_default_engines_option(const char* name, int64_t value)
+{
+	std::lock_guard<std::mutex> lock(g_mu);
+	if (g_pool.empty()) {
+		/* validate the name on a throw-away basis: an unknown option must fail now, not at the first ssw_align */
+		static const char* known[] = {"slices", "latency_cols", "parts", "small_chunk", "chunk", "cm_block", "cm_budget_mb", "grid_min", "inst", "super", "tb_maxbw"};
+		bool ok = false;
+		for (const char* k : known) if (!strcmp(k, name)) ok = true;
+		if (!ok) { fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name); return -1; }
+	}
+	for (PoolEntry& p : g_pool) if (ssw_engine_set_option(p.e, name, value)) return -1;
+	for (auto& kv : g_pool_options) if (kv.first == name) { kv.second = value; return 0; }
+	g_pool_options.emplace_back(name, value);
+	return 0;
+}
 
 extern "C" s_profile* ssw_init(const int8_t* read, const int32_t readLen, const int8_t* mat, const int32_t n, const int8_t score_size)
 {
@@ -83,24 +156,29 @@ extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t 
                               const uint8_t weight_gapO, const uint8_t weight_gapE, const uint8_t flag,
                               const uint16_t filters, const int32_t filterd, const int32_t maskLen)
 {
-	if (!prof) return NULL;
+	if (!prof || !ref || refLen < 0 || prof->readLen < 1 || !prof->read || !prof->mat) return NULL;
 	if (maskLen < 15)   /* ssw.c:876-878: printed on every call */
 		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
-	std::lock_guard<std::mutex> lock(g_mu);
-	ssw_engine* e = default_engine();
-	if (!e) return NULL;
-	const int64_t qoff[2] = {0, prof->readLen}, roff[2] = {0, refLen};
-	if (ssw_engine_set_sequences(e, 1, prof->read, qoff, 1, ref, roff)) return NULL;
-	ssw_batch_params P;
-	memset(&P, 0, sizeof(P));
-	P.mat = prof->mat; P.n = prof->n; P.gap_open = weight_gapO; P.gap_extend = weight_gapE;
-	P.flag = flag; P.filters = filters; P.filterd = filterd; P.mask_len = maskLen < 0 ? 0 : maskLen; P.score_size = prof->score_size;
-	ssw_batch_result r;
-	std::vector<uint32_t> pool((size_t)prof->readLen + (size_t)refLen + 8);
-	int64_t used = 0;
-	const int32_t pq = 0, pr = 0;
-	if (ssw_engine_align(e, &P, 1, &pq, &pr, &r, pool.data(), (int64_t)pool.size(), &used)) return NULL;
-	return record_from(r, pool.data());
+	try {
+		PoolGuard g(pool_acquire(ref, refLen));
+		ssw_engine* e = g.e;
+		if (!e) return NULL;
+		if (ssw_engine_set_pair(e, prof->read, prof->readLen, ref, refLen)) return NULL;
+		ssw_batch_params P;
+		memset(&P, 0, sizeof(P));
+		P.mat = prof->mat; P.n = prof->n; P.gap_open = weight_gapO; P.gap_extend = weight_gapE;
+		P.flag = flag; P.filters = filters; P.filterd = filterd; P.mask_len = maskLen < 0 ? 0 : maskLen; P.score_size = prof->score_size;
+		ssw_batch_result r;
+		/* uninitialised storage: only the words the traceback writes are read */
+		const size_t cap = (flag & 7) ? (size_t)prof->readLen + (size_t)refLen + 8 : 8;
+		std::unique_ptr<uint32_t[]> pool(new uint32_t[cap]);
+		int64_t used = 0;
+		const int32_t pq = 0, pr = 0;
+		if (ssw_engine_align(e, &P, 1, &pq, &pr, &r, pool.get(), (int64_t)cap, &used)) return NULL;
+		return record_from(r, pool.get());
+	}
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_align: %s\n", ex.what()); return NULL; }
+	catch (...) { return NULL; }
 }
 
 namespace {
@@ -108,6 +186,7 @@ namespace {
 int collect_batch(ssw_engine* e, const ssw_batch_params* params, int32_t n_queries, const int64_t* query_off,
                   int32_t n_refs, const int64_t* ref_off, int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out)
 {
+	if (n_pairs < 0 || (n_pairs > 0 && (n_queries <= 0 || n_refs <= 0))) return -1;
 	std::vector<ssw_batch_result> res((size_t)n_pairs);
 	int64_t cap = 0;
 	if (params->flag & 7) {
@@ -139,17 +218,18 @@ extern "C" int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
                                s_align** out)
 {
 	if (!params || !out) return -1;
-	std::unique_lock<std::mutex> lock(g_mu, std::defer_lock);
-	if (!e) {                                   /* NULL: the process-wide engine that also serves ssw_align */
-		lock.lock();
-		e = default_engine();
+	try {
+		PoolGuard g(e ? nullptr : pool_acquire(nullptr, 0));       /* NULL: an engine of the pool that also serves ssw_align */
+		if (!e) e = g.e;
 		if (!e) return -1;
+		if (params->mask_len >= 0 && params->mask_len < 15)
+			fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+		const int rc = ssw_engine_set_sequences(e, n_queries, queries, query_off, n_refs, refs, ref_off);
+		if (rc) return rc;
+		return collect_batch(e, params, n_queries, query_off, n_refs, ref_off, n_pairs, pair_query, pair_ref, out);
 	}
-	if (params->mask_len >= 0 && params->mask_len < 15)
-		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
-	const int rc = ssw_engine_set_sequences(e, n_queries, queries, query_off, n_refs, refs, ref_off);
-	if (rc) return rc;
-	return collect_batch(e, params, n_queries, query_off, n_refs, ref_off, n_pairs, pair_query, pair_ref, out);
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_align_batch: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
 }
 
 extern "C" int ssw_align_batch_text(ssw_engine* e, const ssw_batch_params* params, const int8_t* table, int32_t add_reverse_complement,
@@ -159,21 +239,23 @@ extern "C" int ssw_align_batch_text(ssw_engine* e, const ssw_batch_params* param
                                     s_align** out)
 {
 	if (!params || !out || !table) return -1;
-	std::unique_lock<std::mutex> lock(g_mu, std::defer_lock);
-	if (!e) {
-		lock.lock();
-		e = default_engine();
+	try {
+		PoolGuard g(e ? nullptr : pool_acquire(nullptr, 0));
+		if (!e) e = g.e;
 		if (!e) return -1;
+		if (params->mask_len >= 0 && params->mask_len < 15)
+			fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+		const int rc = ssw_engine_set_sequences_text(e, n_queries, queries, query_off, n_refs, refs, ref_off, table, params->n, add_reverse_complement);
+		if (rc) return rc;
+		if (n_queries <= 0 || !query_off) return n_pairs == 0 ? 0 : -1;
+		/* query k + n_queries is the reverse complement of query k */
+		const int32_t nq = n_queries * (add_reverse_complement ? 2 : 1);
+		std::vector<int64_t> qoff(query_off, query_off + n_queries + 1);
+		if (add_reverse_complement) for (int i = 1; i <= n_queries; ++i) qoff.push_back(query_off[n_queries] + query_off[i]);
+		return collect_batch(e, params, nq, qoff.data(), n_refs, ref_off, n_pairs, pair_query, pair_ref, out);
 	}
-	if (params->mask_len >= 0 && params->mask_len < 15)
-		fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
-	const int rc = ssw_engine_set_sequences_text(e, n_queries, queries, query_off, n_refs, refs, ref_off, table, params->n, add_reverse_complement);
-	if (rc) return rc;
-	/* query k + n_queries is the reverse complement of query k */
-	const int32_t nq = n_queries * (add_reverse_complement ? 2 : 1);
-	std::vector<int64_t> qoff(query_off, query_off + n_queries + 1);
-	if (add_reverse_complement) for (int i = 1; i <= n_queries; ++i) qoff.push_back(query_off[n_queries] + query_off[i]);
-	return collect_batch(e, params, nq, qoff.data(), n_refs, ref_off, n_pairs, pair_query, pair_ref, out);
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_align_batch_text: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
 }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -62,6 +62,8 @@ static inline void ssw_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 /* ---- geometry constants ---------------------------------------------------- */
 #define SSW_REF_PAD 64          /* null letters stored before and after every reference */
 #define SSW_NEG16 (-32768)      /* score of dead rows / null letters: keeps H at exactly 0 */
+#define SSW_CM_NONE ((int64_t)(-0x7fffffffffffffffLL - 1))   /* cm_off value: no column maxima are recorded */
+#define SSW_CM_BLOCK 64         /* columns per block of the block-maximum mode (CM == 2) of the fill kernel */
 
 /* ---- packed s16x2 helpers --------------------------------------------------- */
 __host__ __device__ static __forceinline__ uint32_t pack2(int lo, int hi)
@@ -94,7 +96,8 @@ struct SswItem {
 	int32_t p0, p1;     /* counted scan range */
 	int32_t warm;       /* warm-up scan positions before p0 (state build-up, results discarded) */
 	int32_t term_a;     /* reverse pass: stop once a column maximum equals this (score1); else -1 */
-	int64_t cm_off;     /* offset (in uint32 words) of this pair-task's column-maximum row; -1: none */
+	int64_t cm_off;     /* offset (in uint32 words) of this pair-task's column-maximum row (block mode: of its row of
+	                     * block maxima); SSW_CM_NONE: none.  May be negative for the re-fill items of the block mode. */
 };
 
 /* Per item and half: best cell in scan order = (max score, first scan index, smallest row). */
@@ -117,7 +120,7 @@ struct SswAlnDesc {
 	int32_t mask_len;
 	int64_t cm_off;     /* as in SswItem */
 	int32_t scan_all;   /* 1: item records are not column-maximum summaries (strip-pipelined fill): scan every column */
-	int32_t pad_;
+	int32_t warm;       /* block mode: warm-up columns a re-fill of one block of this pair-task needs */
 };
 
 /* Output of the resolve kernel (the reference's alignment_end[2], ssw.c:104-108, plus status). */

@@ -13,6 +13,8 @@
  * Nothing here computes alignments on the CPU; all DP work is in the kernels.
  */
 #include <algorithm>
+#include <exception>
+#include <mutex>
 #include <vector>
 #include <string>
 #include <string.h>
@@ -55,15 +57,24 @@ static const Inst kInst[] = {
 static const int kNumFwd = 10;
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 
-static int g_slices = 0;           /* "slices" option: 0 automatic, 1 never slice a batch over helper engines, 2/3 forced (tests) */
-static int g_strip_parts = 0;      /* "parts" option: 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
-static int g_strip_super = SSW_STRIP_SUPER;   /* columns per super-block of the strip kernel ("super" option, tests) */
-static int g_grid_min_pairs = 32768;    /* "grid_min" option: smaller grids use the general path */
-static int64_t g_latency_cols = 1 << 20;   /* "latency_cols" option: passes over at most this many reference columns use the 32-lane instances */
-static int g_force_inst = -1;      /* "inst" option (measurements): use this forward instance whenever it covers the query */
-static int pick_inst(int lp)
+/* Tuning knobs ("ssw_engine_set_option"); every engine has its own copy (helper engines get their parent's). */
+struct SswOptions {
+	int slices = 0;                 /* "slices": 0 automatic, 1 never slice a batch over helper engines, 2/3 forced (tests) */
+	int strip_parts = 0;            /* "parts": 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
+	int strip_super = SSW_STRIP_SUPER;   /* "super": columns per super-block of the strip kernel (tests) */
+	int grid_min_pairs = 32768;     /* "grid_min": smaller grids use the general path */
+	int64_t latency_cols = 1 << 20; /* "latency_cols": passes over at most this many reference columns use the 32-lane instances */
+	int force_inst = -1;            /* "inst" (measurements): use this forward instance whenever it covers the query */
+	int tb_maxbw = SSW_TBP_MAXBW;   /* "tb_maxbw": widest band handled by the shared-memory traceback kernel */
+	int cm_block = -1;              /* "cm_block": -1 automatic, 0 one word per column always, 1 block maxima wherever chunking is possible (tests) */
+	int64_t chunk = 0;              /* "chunk": reference chunk length of the fill kernel (0 automatic) */
+	int64_t small_chunk = 0;        /* "small_chunk" (measurements): chunk length of launches too small to fill the device */
+	int64_t cm_budget = 0;          /* "cm_budget_mb": cap of the column-maximum scratch per launch in bytes (0: half of the free memory; tests) */
+};
+
+static int pick_inst(int lp, int force_inst)
 {
-	if (g_force_inst >= 0 && g_force_inst < kNumInst && kInst[g_force_inst].G * kInst[g_force_inst].R >= lp) return g_force_inst;   /* 10..13: the 32-lane layouts */
+	if (force_inst >= 0 && force_inst < kNumInst && kInst[force_inst].G * kInst[force_inst].R >= lp) return force_inst;   /* 10..13: the 32-lane layouts */
 	for (int i = 0; i < kNumFwd; ++i) if (kInst[i].G * kInst[i].R >= lp) return i;
 	return -1;
 }
@@ -92,21 +103,23 @@ struct ssw_engine {
 	std::vector<int64_t> h_r_off;
 	int padded_n = -1;               /* null letter currently stored in the reference pads */
 	bool from_text = false;          /* sequences were translated on the device: no host copy to re-pad from */
+	int64_t cached_ref_len = -1;     /* ssw_engine_set_pair: length and content hash of the single resident reference (-1: none) */
+	uint64_t cached_ref_hash = 0;
 	SswDevBuf d_q, d_r, d_mat;
 
 	/* scratch */
 	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out, d_sync;
+	SswDevBuf d_rf_items, d_rf_bests, d_rf_blk, d_rf_cm;     /* block-maximum mode: re-fill items, their (unused) bests, block ids, column maxima */
 	SswStagedD2H staged;
 	cudaStream_t side[3] = {nullptr, nullptr, nullptr};     /* traceback launches of different kernel shapes run side by side */
 	ssw_engine* kids[3] = {nullptr, nullptr, nullptr};      /* helper engines of the sliced path (views of this engine's sequences) */
 	bool is_kid = false;
-	int64_t opt_chunk = 0;
-	int64_t opt_small_chunk = 0;        /* "small_chunk" option (measurements): chunk length of launches too small to fill the device */
+	SswOptions opt;
 	ssw_engine_timing timing;
 	SswTimer t_total, t_k;
 
 	int upload_refs(int n);
-	int run_fill(const std::vector<SswItem>& items, int inst, int dir, int share, const ssw_batch_params& P, float* ms_acc);
+	int run_fill(const std::vector<SswItem>& items, int inst, int dir, int cm_mode, int share, const ssw_batch_params& P, float* ms_acc);
 };
 
 
@@ -114,8 +127,10 @@ struct ssw_engine {
 /* fill kernel dispatch                                                                          */
 /* ------------------------------------------------------------------------------------------- */
 
+struct FillPtrs { const SswItem* items; uint32_t* cm; SswItemBest* bests; };
+
 template <int G, int R>
-static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw_batch_params& P)
+static int launch_fill(ssw_engine* e, const FillPtrs& fp, int n_items, int dir, int cm_mode, int share, const ssw_batch_params& P)
 {
 	constexpr int GPW = 32 / G;
 	/* per-warp profiles (share == 0) can be large for big alphabets: use fewer warps per CTA then */
@@ -126,12 +141,12 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw
 	const int grid = (n_items + per_cta - 1) / per_cta;
 	const size_t smem = share ? warp_smem : warp_smem * warps;
 	if (smem > 220 * 1024) { fprintf(stderr, "[libssw-b200] alphabet of %d letters is too large for this query length\n", P.n); return -2; }
-	const SswItem* items = e->d_items.as<SswItem>();
+	const SswItem* items = fp.items;
 	const int8_t* q = e->d_q.as<int8_t>();
 	const int8_t* r = e->d_r.as<int8_t>();
 	const int8_t* mat = e->d_mat.as<int8_t>();
-	uint32_t* cm = e->d_colmax.as<uint32_t>();
-	SswItemBest* bests = e->d_bests.as<SswItemBest>();
+	uint32_t* cm = fp.cm;
+	SswItemBest* bests = fp.bests;
 #define SSW_FILL_GO(DIR, CM, TERM)                                                                               \
 	do {                                                                                                         \
 		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM>;                                                        \
@@ -139,9 +154,9 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw
 		ssw_launch(kern, dim3(grid), dim3(warps * 32), smem, e->stream, items, n_items, q, r, mat, (int)P.n,     \
 		           (int)P.gap_open, (int)P.gap_extend, cm, bests, share);                                        \
 	} while (0)
-	if (dir > 0) SSW_FILL_GO(1, true, false);           /* forward: column maxima always recorded */
+	if (dir > 0) { if (cm_mode == 2) SSW_FILL_GO(1, 2, false); else SSW_FILL_GO(1, 1, false); }   /* forward: column maxima per column or per block */
 	else {
-		if constexpr (G == 32) SSW_FILL_GO(-1, false, true);   /* reverse: one alignment per warp, early termination */
+		if constexpr (G == 32) SSW_FILL_GO(-1, 0, true);   /* reverse: one alignment per warp, early termination */
 		else return -2;
 	}
 #undef SSW_FILL_GO
@@ -149,7 +164,29 @@ static int launch_fill(ssw_engine* e, int n_items, int dir, int share, const ssw
 	return 0;
 }
 
-int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, int share, const ssw_batch_params& P, float* ms_acc)
+static int dispatch_fill(ssw_engine* e, int inst, const FillPtrs& fp, int n_items, int dir, int cm_mode, int share, const ssw_batch_params& P)
+{
+	switch (inst) {
+	case 0: return launch_fill<8, 4>(e, fp, n_items, dir, cm_mode, share, P);
+	case 1: return launch_fill<8, 5>(e, fp, n_items, dir, cm_mode, share, P);
+	case 2: return launch_fill<8, 8>(e, fp, n_items, dir, cm_mode, share, P);
+	case 3: return launch_fill<8, 10>(e, fp, n_items, dir, cm_mode, share, P);
+	case 4: return launch_fill<8, 16>(e, fp, n_items, dir, cm_mode, share, P);
+	case 5: return launch_fill<8, 20>(e, fp, n_items, dir, cm_mode, share, P);
+	case 6: return launch_fill<16, 16>(e, fp, n_items, dir, cm_mode, share, P);
+	case 7: return launch_fill<16, 20>(e, fp, n_items, dir, cm_mode, share, P);
+	case 8: return launch_fill<32, 16>(e, fp, n_items, dir, cm_mode, share, P);
+	case 9: return launch_fill<32, 20>(e, fp, n_items, dir, cm_mode, share, P);
+	case 10: return launch_fill<32, 4>(e, fp, n_items, dir, cm_mode, share, P);      /* 10..13: the 32-lane layouts (reverse pass, latency path, "inst" option) */
+	case 11: return launch_fill<32, 5>(e, fp, n_items, dir, cm_mode, share, P);
+	case 12: return launch_fill<32, 8>(e, fp, n_items, dir, cm_mode, share, P);
+	case 13: return launch_fill<32, 10>(e, fp, n_items, dir, cm_mode, share, P);
+	default: break;
+	}
+	return -1;
+}
+
+int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, int cm_mode, int share, const ssw_batch_params& P, float* ms_acc)
 {
 	const int n_items = (int)items.size();
 	if (n_items == 0) return 0;
@@ -159,24 +196,8 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, i
 	SSW_CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), sizeof(SswItem) * items.size(), cudaMemcpyHostToDevice, stream));
 	tr.lap("  fill: items h2d");
 	t_k.start(stream);
-	int rc = -1;
-	switch (inst) {
-	case 0: rc = launch_fill<8, 4>(this, n_items, dir, share, P); break;
-	case 1: rc = launch_fill<8, 5>(this, n_items, dir, share, P); break;
-	case 2: rc = launch_fill<8, 8>(this, n_items, dir, share, P); break;
-	case 3: rc = launch_fill<8, 10>(this, n_items, dir, share, P); break;
-	case 4: rc = launch_fill<8, 16>(this, n_items, dir, share, P); break;
-	case 5: rc = launch_fill<8, 20>(this, n_items, dir, share, P); break;
-	case 6: rc = launch_fill<16, 16>(this, n_items, dir, share, P); break;
-	case 7: rc = launch_fill<16, 20>(this, n_items, dir, share, P); break;
-	case 8: rc = launch_fill<32, 16>(this, n_items, dir, share, P); break;
-	case 9: rc = launch_fill<32, 20>(this, n_items, dir, share, P); break;
-	case 10: rc = launch_fill<32, 4>(this, n_items, dir, share, P); break;
-	case 11: rc = launch_fill<32, 5>(this, n_items, dir, share, P); break;
-	case 12: rc = launch_fill<32, 8>(this, n_items, dir, share, P); break;
-	case 13: rc = launch_fill<32, 10>(this, n_items, dir, share, P); break;
-	default: break;
-	}
+	const FillPtrs fp = {d_items.as<SswItem>(), d_colmax.as<uint32_t>(), d_bests.as<SswItemBest>()};
+	const int rc = dispatch_fill(this, inst, fp, n_items, dir, cm_mode, share, P);
 	tr.lap("  fill: launch");
 	*ms_acc += t_k.stop(stream);
 	tr.lap("  fill: wait");
@@ -190,7 +211,7 @@ static int fill_occ_of(int n)
 {
 	int occ = 0;
 	const size_t smem = ssw_fill_smem_bytes<R>(n, 1);
-	auto kern = ssw_fill_kernel<G, R, 1, true, false>;
+	auto kern = ssw_fill_kernel<G, R, 1, 2, false>;
 	ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSW_FILL_THREADS, smem) != cudaSuccess) occ = 1;
 	return occ;
@@ -198,7 +219,9 @@ static int fill_occ_of(int n)
 static int fill_occupancy(int inst, int n)
 {
 	static int cache[16][65];
+	static std::mutex mu;
 	if (inst < 0 || inst >= 16 || n < 0 || n > 64) return 1;
+	std::lock_guard<std::mutex> lock(mu);
 	if (cache[inst][n]) return cache[inst][n];
 	int occ = 1;
 	switch (inst) {
@@ -242,6 +265,7 @@ extern "C" ssw_engine* ssw_engine_create(int device)
 	e->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
 	memset(&e->timing, 0, sizeof(e->timing));
+	++ssw_live_engines();
 	return e;
 }
 
@@ -249,12 +273,13 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 {
 	if (!e) return;
 	cudaSetDevice(e->device);
-	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out, &e->d_sync};
+	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out, &e->d_sync, &e->d_rf_items, &e->d_rf_bests, &e->d_rf_blk, &e->d_rf_cm};
 	for (SswDevBuf* b : bufs) b->release();
 	for (ssw_engine*& k : e->kids) if (k) { ssw_engine_destroy(k); k = nullptr; }
 	e->staged.release();
 	for (cudaStream_t& st : e->side) if (st) { cudaStreamDestroy(st); st = nullptr; }
 	if (e->stream) cudaStreamDestroy(e->stream);
+	--ssw_live_engines();
 	delete e;
 }
 
@@ -262,16 +287,20 @@ extern "C" const char* ssw_engine_device_name(const ssw_engine* e) { return e ? 
 
 extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value)
 {
-	if (!e || !name) return -1;
-	if (!strcmp(name, "slices")) { g_slices = value >= 1 && value <= 3 ? (int)value : 0; return 0; }
-	if (!strcmp(name, "latency_cols")) { g_latency_cols = value < 0 ? 0 : value; return 0; }
-	if (!strcmp(name, "parts")) { g_strip_parts = value == 1 || value == 2 || value == 4 ? (int)value : 0; return 0; }
-	if (!strcmp(name, "small_chunk")) { e->opt_small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
-	if (!strcmp(name, "chunk")) { e->opt_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
-	if (!strcmp(name, "grid_min")) { g_grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
-	if (!strcmp(name, "inst")) { g_force_inst = (int)value; return 0; }       /* index into kInst */
-	if (!strcmp(name, "super")) { g_strip_super = value >= 64 ? (int)(value + 7) / 8 * 8 : SSW_STRIP_SUPER; return 0; }
-	if (!strcmp(name, "tb_maxbw")) { g_ssw_tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
+	if (!name) return -1;
+	if (!e) return ssw_default_engines_option(name, value);
+	SswOptions& o = e->opt;
+	if (!strcmp(name, "slices")) { o.slices = value >= 1 && value <= 3 ? (int)value : 0; return 0; }
+	if (!strcmp(name, "latency_cols")) { o.latency_cols = value < 0 ? 0 : value; return 0; }
+	if (!strcmp(name, "parts")) { o.strip_parts = value == 1 || value == 2 || value == 4 ? (int)value : 0; return 0; }
+	if (!strcmp(name, "small_chunk")) { o.small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
+	if (!strcmp(name, "chunk")) { o.chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
+	if (!strcmp(name, "cm_block")) { o.cm_block = value < 0 ? -1 : (value ? 1 : 0); return 0; }
+	if (!strcmp(name, "cm_budget_mb")) { o.cm_budget = value <= 0 ? 0 : value << 20; return 0; }
+	if (!strcmp(name, "grid_min")) { o.grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
+	if (!strcmp(name, "inst")) { o.force_inst = (int)value; return 0; }       /* index into kInst */
+	if (!strcmp(name, "super")) { o.strip_super = value >= 64 ? (int)(value + 7) / 8 * 8 : SSW_STRIP_SUPER; return 0; }
+	if (!strcmp(name, "tb_maxbw")) { o.tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;
 }
@@ -311,39 +340,111 @@ int ssw_engine::upload_refs(int n)
 	return 0;
 }
 
-extern "C" int ssw_engine_set_sequences(ssw_engine* e,
-                                        int32_t n_queries, const int8_t* queries, const int64_t* query_off,
-                                        int32_t n_refs, const int8_t* refs, const int64_t* ref_off)
+/* Offsets must be non-decreasing and start at 0; device-side descriptors hold 32-bit query offsets and reference lengths. */
+static int check_offsets(const char* what, int32_t n, const int64_t* off, int64_t limit_total, int64_t limit_each)
+{
+	if (n == 0) return 0;
+	if (!off || off[0] != 0) { fprintf(stderr, "[libssw-b200] %s offsets must start at 0\n", what); return -1; }
+	for (int32_t i = 0; i < n; ++i) {
+		if (off[i + 1] < off[i]) { fprintf(stderr, "[libssw-b200] %s offsets are not non-decreasing at %d\n", what, i); return -1; }
+		if (off[i + 1] - off[i] > limit_each) { fprintf(stderr, "[libssw-b200] %s %d is longer than %lld\n", what, i, (long long)limit_each); return -1; }
+	}
+	if (off[n] > limit_total) { fprintf(stderr, "[libssw-b200] %s hold %lld letters in total; the limit is %lld\n", what, (long long)off[n], (long long)limit_total); return -1; }
+	return 0;
+}
+#define SSW_MAX_QUERY_LETTERS ((int64_t)0x7fffffff - 64)                        /* SswQuery.off is 32 bits */
+#define SSW_MAX_REF_LEN ((int64_t)0x7fffffff - 4 * SSW_REF_PAD - 64)            /* SswItem.ref_len, scan positions */
+
+static int set_sequences_impl(ssw_engine* e,
+                              int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                              int32_t n_refs, const int8_t* refs, const int64_t* ref_off)
 {
 	if (!e || n_queries < 0 || n_refs < 0 || (n_queries && (!queries || !query_off)) || (n_refs && (!refs || !ref_off))) return -1;
+	if (check_offsets("query", n_queries, query_off, SSW_MAX_QUERY_LETTERS, SSW_MAX_QUERY_LETTERS)) return -1;
+	if (check_offsets("reference", n_refs, ref_off, (int64_t)1 << 46, SSW_MAX_REF_LEN)) return -1;
 	SSW_CUDA_OK(cudaSetDevice(e->device));
 	e->n_q = n_queries; e->n_r = n_refs;
 	e->from_text = false;
-	e->q_off.assign(query_off, query_off + n_queries + 1);
-	e->h_q.assign(queries, queries + query_off[n_queries]);
-	e->h_r_off.assign(ref_off, ref_off + n_refs + 1);
-	e->h_r.assign(refs, refs + ref_off[n_refs]);
+	e->cached_ref_len = -1;
+	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
+	if (n_queries) e->q_off.assign(query_off, query_off + n_queries + 1); else e->q_off.assign(1, 0);
+	e->h_q.assign(queries, queries + qb);
+	if (n_refs) e->h_r_off.assign(ref_off, ref_off + n_refs + 1); else e->h_r_off.assign(1, 0);
+	e->h_r.assign(refs, refs + rb);
 	e->r_len.resize(n_refs);
 	for (int i = 0; i < n_refs; ++i) e->r_len[i] = (int32_t)(ref_off[i + 1] - ref_off[i]);
 	if (e->d_q.ensure(e->h_q.size() + 16)) return -1;
-	SSW_CUDA_OK(cudaMemcpyAsync(e->d_q.p, e->h_q.data(), e->h_q.size(), cudaMemcpyHostToDevice, e->stream));
+	if (qb) SSW_CUDA_OK(cudaMemcpyAsync(e->d_q.p, e->h_q.data(), e->h_q.size(), cudaMemcpyHostToDevice, e->stream));
 	e->padded_n = -1;           /* the null letter depends on the alphabet size given at align time */
 	return 0;
 }
 
+extern "C" int ssw_engine_set_sequences(ssw_engine* e,
+                                        int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                                        int32_t n_refs, const int8_t* refs, const int64_t* ref_off)
+{
+	try { return set_sequences_impl(e, n_queries, queries, query_off, n_refs, refs, ref_off); }
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_set_sequences: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
+}
+
+/* One query against one reference, as ssw_align sees it.  The reference's consumers loop over many reads against one large
+ * reference (main.c:462-532, ssw_cpp.cpp:336); when the bytes at `ref` are the ones already resident (same length, same 64-bit
+ * content hash) only the query is uploaded -- no host copy, no re-padding, no H2D of the reference. */
+extern "C" int ssw_engine_set_pair(ssw_engine* e, const int8_t* read, int32_t readLen, const int8_t* ref, int32_t refLen)
+{
+	if (!e || !read || !ref || readLen < 1 || refLen < 0) return -1;
+	try {
+		const uint64_t h = ssw_hash_bytes(ref, (size_t)refLen);
+		const bool same = e->n_r == 1 && !e->from_text && e->cached_ref_len == (int64_t)refLen && e->cached_ref_hash == h && e->d_r.p;
+		if (!same) {
+			const int64_t qoff[2] = {0, readLen}, roff[2] = {0, refLen};
+			const int rc = set_sequences_impl(e, 1, read, qoff, 1, ref, roff);
+			if (rc) return rc;
+			e->cached_ref_len = refLen; e->cached_ref_hash = h;
+			return 0;
+		}
+		SSW_CUDA_OK(cudaSetDevice(e->device));
+		e->n_q = 1;
+		e->q_off.assign(2, 0); e->q_off[1] = readLen;
+		e->h_q.assign(read, read + readLen);
+		if (e->d_q.ensure(e->h_q.size() + 16)) return -1;
+		SSW_CUDA_OK(cudaMemcpyAsync(e->d_q.p, e->h_q.data(), e->h_q.size(), cudaMemcpyHostToDevice, e->stream));
+		return 0;
+	}
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_set_pair: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
+}
+
+static int set_sequences_text_impl(ssw_engine* e,
+                                   int32_t n_queries, const char* queries, const int64_t* query_off,
+                                   int32_t n_refs, const char* refs, const int64_t* ref_off,
+                                   const int8_t* table, int32_t n, int32_t add_reverse_complement);
 extern "C" int ssw_engine_set_sequences_text(ssw_engine* e,
                                              int32_t n_queries, const char* queries, const int64_t* query_off,
                                              int32_t n_refs, const char* refs, const int64_t* ref_off,
                                              const int8_t* table, int32_t n, int32_t add_reverse_complement)
 {
+	try { return set_sequences_text_impl(e, n_queries, queries, query_off, n_refs, refs, ref_off, table, n, add_reverse_complement); }
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_set_sequences_text: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
+}
+static int set_sequences_text_impl(ssw_engine* e,
+                                   int32_t n_queries, const char* queries, const int64_t* query_off,
+                                   int32_t n_refs, const char* refs, const int64_t* ref_off,
+                                   const int8_t* table, int32_t n, int32_t add_reverse_complement)
+{
 	if (!e || !table || n < 1 || n > 64 || n_queries < 0 || n_refs < 0 || (n_queries && (!queries || !query_off)) ||
 	    (n_refs && (!refs || !ref_off)))
 		return -1;
-	SSW_CUDA_OK(cudaSetDevice(e->device));
-	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
 	const int rc = add_reverse_complement ? 1 : 0;
+	if (check_offsets("query", n_queries, query_off, SSW_MAX_QUERY_LETTERS / (1 + rc), SSW_MAX_QUERY_LETTERS / (1 + rc))) return -1;
+	if (check_offsets("reference", n_refs, ref_off, (int64_t)1 << 46, SSW_MAX_REF_LEN)) return -1;
+	SSW_CUDA_OK(cudaSetDevice(e->device));
+	e->cached_ref_len = -1;
+	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
 	e->n_q = n_queries * (1 + rc); e->n_r = n_refs;
-	e->q_off.assign(query_off, query_off + n_queries + 1);
+	if (n_queries) e->q_off.assign(query_off, query_off + n_queries + 1); else e->q_off.assign(1, 0);
 	if (rc) for (int i = 1; i <= n_queries; ++i) e->q_off.push_back(qb + query_off[i]);
 	e->h_q.clear(); e->h_r.clear(); e->h_r_off.clear();
 	e->r_len.resize(n_refs);
@@ -424,8 +525,12 @@ static inline bool needs_other(const SswFillResult& r, int word, const Sem& S, b
 	return word_first && S.has_byte && r.overflow == 0 && r.score < S.limit_byte;
 }
 
-/* Launch the resolve kernel over `descs` and fetch the results. */
-static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool second, std::vector<SswFillResult>& res)
+/* How the column maxima of the fill being resolved are stored (fill kernel CM mode), and -- block mode -- what the
+ * re-fill of single blocks needs: the kernel instance of the fill and the scoring parameters. */
+struct CmMode { int block; int inst; const ssw_batch_params* P; };
+
+/* Launch the resolve kernel(s) over `descs` and fetch the results. */
+static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool second, std::vector<SswFillResult>& res, const CmMode* cm = nullptr)
 {
 	res.resize(descs.size());
 	if (descs.empty()) return 0;
@@ -435,7 +540,25 @@ static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool
 	e->t_k.start(e->stream);
 	const int per = SSW_RESOLVE_THREADS / 32;
 	const dim3 grid(((int)descs.size() + per - 1) / per);
-	if (second)
+	if (second && cm && cm->block) {
+		/* block maxima: stage 1 (summaries + the three blocks per alignment that need single columns), re-fill of those
+		 * blocks with one word per column, stage 2 */
+		const size_t n_rf = descs.size() * SSW_REFILL_SLOTS;
+		if (e->d_rf_items.ensure(sizeof(SswItem) * n_rf)) return -1;
+		if (e->d_rf_bests.ensure(sizeof(SswItemBest) * n_rf)) return -1;
+		if (e->d_rf_blk.ensure(sizeof(int32_t) * n_rf)) return -1;
+		if (e->d_rf_cm.ensure(sizeof(uint32_t) * n_rf * SSW_CM_BLOCK + 64)) return -1;
+		ssw_launch(ssw_resolve_blocks_kernel<0>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
+		           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)e->d_colmax.as<uint32_t>(),
+		           (const SswItem*)e->d_items.as<SswItem>(), e->d_res.as<SswFillResult>(), e->d_rf_items.as<SswItem>(), e->d_rf_blk.as<int32_t>());
+		SSW_CUDA_OK(cudaGetLastError());
+		const FillPtrs fp = {e->d_rf_items.as<SswItem>(), e->d_rf_cm.as<uint32_t>(), e->d_rf_bests.as<SswItemBest>()};
+		const int rc = dispatch_fill(e, cm->inst, fp, (int)n_rf, +1, 1, 0, *cm->P);
+		if (rc) return rc < 0 ? rc : -1;
+		ssw_launch(ssw_resolve_refill_kernel<0>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
+		           (int)descs.size(), (const int32_t*)e->d_rf_blk.as<int32_t>(), (const uint32_t*)e->d_rf_cm.as<uint32_t>(), e->d_res.as<SswFillResult>());
+		e->timing.other_launches += 2;
+	} else if (second)
 		ssw_launch(ssw_resolve_kernel<true>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
 		           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)e->d_colmax.as<uint32_t>(), e->d_res.as<SswFillResult>());
 	else
@@ -456,10 +579,10 @@ static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool
  * `refill` for a fill with the other row count.
  */
 static int resolve_forward(ssw_engine* e, std::vector<SswAlnDesc>& descs, const std::vector<int64_t>& desc_aln, std::vector<Aln>& alns,
-                           int word, const Sem& S, bool word_first, std::vector<int64_t>* refill)
+                           int word, const Sem& S, bool word_first, std::vector<int64_t>* refill, const CmMode* cm = nullptr)
 {
 	std::vector<SswFillResult> res;
-	if (run_resolve(e, descs, true, res)) return -1;
+	if (run_resolve(e, descs, true, res, cm)) return -1;
 	std::vector<SswAlnDesc> alt;
 	std::vector<int64_t> alt_aln;
 	for (size_t i = 0; i < descs.size(); ++i) {
@@ -475,7 +598,7 @@ static int resolve_forward(ssw_engine* e, std::vector<SswAlnDesc>& descs, const 
 		} else if (refill) refill->push_back(desc_aln[i]);
 	}
 	if (!alt.empty()) {
-		if (run_resolve(e, alt, true, res)) return -1;
+		if (run_resolve(e, alt, true, res, cm)) return -1;
 		for (size_t i = 0; i < alt.size(); ++i) { alns[alt_aln[i]].fwd = res[i]; alns[alt_aln[i]].word = alt[i].word; }
 	}
 	return 0;
@@ -523,10 +646,10 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		int parts = 1, nw = 1;
 		{
 			double best_cost = 1e300;
-			const bool may_split = dir > 0 && !term && g_strip_parts != 1;
-			const bool forced = may_split && g_strip_parts > 1 && (n_strips + g_strip_parts - 1) / g_strip_parts >= 2;
+			const bool may_split = dir > 0 && !term && e->opt.strip_parts != 1;
+			const bool forced = may_split && e->opt.strip_parts > 1 && (n_strips + e->opt.strip_parts - 1) / e->opt.strip_parts >= 2;
 			for (int pp = 1; pp <= (may_split ? 4 : 1); pp *= 2) {
-				if (forced && pp != g_strip_parts) continue;
+				if (forced && pp != e->opt.strip_parts) continue;
 				const int per = (n_strips + pp - 1) / pp;
 				if (pp > 1 && per < 2) break;
 				const int wmax = std::min(nw_cap, per);
@@ -549,7 +672,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		size_t cm_words = 0, bnd_words = 0, park_words = 0;
 		int n_best = 0;
 		const size_t free_b = ssw_free_device_bytes();
-		const size_t budget = std::max<size_t>((size_t)256 << 20, (free_b + e->d_bnd.cap + e->d_colmax.cap) / 2);
+		const size_t budget = std::max<size_t>((size_t)256 << 20, ssw_budget_share(free_b + e->d_bnd.cap + e->d_colmax.cap));
 		for (; k < order.size() && strips_of(reqs[order[k]]) == n_strips; ++k) {
 			const StripReq& q = reqs[order[k]];
 			SswStripTask T;
@@ -562,12 +685,12 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 				T.p1 = std::max(q.p1, q.p1_b);
 			}
 			T.n_strips = n_strips;
-			T.super = g_strip_super;
+			T.super = e->opt.strip_super;
 			T.n_super = term ? std::max(1, (T.p1 + T.super - 1) / T.super) : 1;
 			T.bnd_len = ((T.p1 + 7) / 8 * 8) + 2 * SSW_STRIP_BPAD + 64;
 			const size_t need = 4 * (cm_words + bnd_words + park_words + 6 * (size_t)T.bnd_len + (size_t)T.p1 + 8);
 			if (!tasks.empty() && need > budget) break;
-			T.cm_off = dir > 0 ? (int64_t)cm_words : -1;
+			T.cm_off = dir > 0 ? (int64_t)cm_words : SSW_CM_NONE;
 			T.bnd_off = (int64_t)bnd_words;
 			T.park_off = (int64_t)park_words;
 			T.first_best = n_best;
@@ -646,13 +769,13 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	 * query ~4x faster than (8,20), which is the better shape once there is enough work).  This is what a one-pair
 	 * ssw_align call gets. */
 	int64_t pass_cols = 0;
-	for (size_t i = 0; i < sel.size() && pass_cols <= g_latency_cols; ++i) pass_cols += alns[sel[i]].ref_len;
-	const bool latency = g_force_inst < 0 && pass_cols <= g_latency_cols;
+	for (size_t i = 0; i < sel.size() && pass_cols <= e->opt.latency_cols; ++i) pass_cols += alns[sel[i]].ref_len;
+	const bool latency = e->opt.force_inst < 0 && pass_cols <= e->opt.latency_cols;
 	for (size_t i = 0; i < sel.size(); ++i) {
 		const Aln& a = alns[sel[i]];
 		const int lp = lp_of(a.read_len, word);
 		int inst = latency ? pick_inst_g32(lp) : -1;
-		if (inst < 0) inst = pick_inst(lp);
+		if (inst < 0) inst = pick_inst(lp, e->opt.force_inst);
 		(inst < 0 ? long_keys : keys).push_back(Key{inst < 0 ? 0 : inst, a.r, a.q, lp, sel[i]});
 	}
 	auto by_ref = [](const Key& x, const Key& y) {
@@ -740,7 +863,8 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	}
 	tr.lap("forward: sort");
 	const size_t free_b = ssw_free_device_bytes();
-	const size_t cm_budget_words = std::max<size_t>((size_t)1 << 22, (free_b + e->d_colmax.cap) / 2 / 4);
+	size_t cm_budget_words = std::max<size_t>((size_t)1 << 22, ssw_budget_share(free_b + e->d_colmax.cap) / 4);
+	if (e->opt.cm_budget > 0) cm_budget_words = std::max<size_t>(1024, (size_t)e->opt.cm_budget / 4);
 	tr.lap("forward: memgetinfo");
 
 	size_t k = 0;
@@ -750,8 +874,20 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 		const int per_cta = SSW_FILL_WARPS * (32 / kInst[inst].G);   /* share == 1 launches always use SSW_FILL_WARPS warps */
 		size_t k_end = k, cm_words = 0;
 		int64_t total_cols = 0;
+		/* Column maxima: one word per column, or -- long references in a launch that fills the device -- one word per block of
+		 * SSW_CM_BLOCK columns plus a re-fill of the three blocks per alignment whose single columns matter (ssw_resolve.cuh).
+		 * The re-fill needs a bounded warm-up, i.e. the same condition as chunking. */
+		bool block = e->opt.cm_block != 0 && P.gap_extend > 0 && S.max_mat > 0;
+		if (block && e->opt.cm_block < 0) {
+			if (latency) block = false;
+			for (size_t i = k; block && i < pts.size() && pts[i].inst == inst; ++i) if (e->r_len[pts[i].r] < 32768) block = false;
+		}
+		const CmMode cm_mode = {block ? 1 : 0, inst, &P};
+		auto cm_words_of = [&](int32_t ref_len) -> size_t {
+			return block ? ((size_t)ref_len / SSW_CM_BLOCK + 1 + 3) / 4 * 4 : ((size_t)ref_len + 3) / 4 * 4;
+		};
 		while (k_end < pts.size() && pts[k_end].inst == inst) {
-			const size_t words = ((size_t)e->r_len[pts[k_end].r] + 3) / 4 * 4;
+			const size_t words = cm_words_of(e->r_len[pts[k_end].r]);
 			if (k_end > k && cm_words + words > cm_budget_words) break;
 			cm_words += words;
 			total_cols += e->r_len[pts[k_end].r];
@@ -782,14 +918,16 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 					/* a launch too small to fill the device (one ssw_align call, the word re-fill of a few overflowed reads) is
 					 * latency-bound: shorter chunks, at the price of more warm-up columns (measured on config 2's re-fill
 					 * launch: 4.07 ms with the 16 x warm-up rule, 3.6 ms with 6 x) */
-					if (e->opt_chunk > 0) chunk = e->opt_chunk;
-					else if (base_chunk < 4096) chunk = e->opt_small_chunk > 0 ? std::max<int64_t>(e->opt_small_chunk, 2 * warm) : std::max<int64_t>(2048, 6 * warm);
+					if (e->opt.chunk > 0) chunk = block ? (e->opt.chunk + SSW_CM_BLOCK - 1) / SSW_CM_BLOCK * SSW_CM_BLOCK : e->opt.chunk;
+					else if (base_chunk < 4096) chunk = e->opt.small_chunk > 0 ? std::max<int64_t>(e->opt.small_chunk, 2 * warm) : std::max<int64_t>(2048, 6 * warm);
 					else chunk = std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
 				}
 				int64_t n_chunks = chunk >= ref_len ? 1 : (ref_len + chunk - 1) / chunk;
-				if (n_chunks > 1 && e->opt_chunk == 0) {
+				if (block) chunk = (chunk + SSW_CM_BLOCK - 1) / SSW_CM_BLOCK * SSW_CM_BLOCK;     /* chunks start at block boundaries */
+				if (n_chunks > 1 && e->opt.chunk == 0) {
 					n_chunks = (n_chunks + per_cta - 1) / per_cta * per_cta;
 					chunk = ((ref_len + n_chunks - 1) / n_chunks + 3) / 4 * 4;
+					if (block) chunk = (chunk + SSW_CM_BLOCK - 1) / SSW_CM_BLOCK * SSW_CM_BLOCK;
 					n_chunks = (ref_len + chunk - 1) / chunk;
 				}
 				if (n_chunks == 1) chunk = std::max<int32_t>((ref_len + 3) / 4 * 4, 4);
@@ -807,7 +945,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 		 * ceil(CTAs / resident CTAs) CTA-times.  Try chunk lengths around the default and keep the one with the best
 		 * (fill of the last wave) x (1 - warm-up overhead). */
 		int64_t auto_chunk = base_chunk;
-		if (e->opt_chunk == 0 && base_chunk >= 4096) {
+		if (e->opt.chunk == 0 && base_chunk >= 4096) {
 			const int occ = fill_occupancy(inst, P.n);
 			const double slots = (double)e->sm_count * std::max(occ, 1);
 			double best_eff = -1;
@@ -844,7 +982,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			if (share && i > k && (pts[i].qa != pts[i - 1].qa || pts[i].qb != pts[i - 1].qb)) {
 				/* the queries change: fill the current CTA with dead items (empty range) of the previous queries */
 				SswItem dead = items.back();
-				dead.p0 = dead.p1 = 0; dead.warm = 0; dead.cm_off = -1;
+				dead.p0 = dead.p1 = 0; dead.warm = 0; dead.cm_off = SSW_CM_NONE;
 				while (items.size() % (size_t)per_cta) items.push_back(dead);
 			}
 			const int first_item = (int)items.size();
@@ -861,19 +999,19 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				SswAlnDesc d;
 				memset(&d, 0, sizeof(d));
 				d.first_item = first_item; d.n_items = pl.n_chunks; d.half = h; d.ref_len = ref_len; d.read_len = X.read_len;
-				d.word = word; d.limit = limit; d.mask_len = X.mask_len; d.cm_off = (int64_t)cm_words;
+				d.word = word; d.limit = limit; d.mask_len = X.mask_len; d.cm_off = (int64_t)cm_words; d.warm = pl.warm;
 				descs.push_back(d);
 				desc_aln.push_back(h ? pt.b : pt.a);
 			}
-			cm_words += ((size_t)ref_len + 3) / 4 * 4;
+			cm_words += cm_words_of(ref_len);
 		}
 		tr.lap("forward: plan");
 		if (e->d_colmax.ensure(cm_words * 4 + 64)) return -1;
-		if (e->run_fill(items, inst, +1, share, P, &e->timing.fill_forward_ms)) return -1;
+		if (e->run_fill(items, inst, +1, block ? 2 : 1, share, P, &e->timing.fill_forward_ms)) return -1;
 		tr.lap("forward: fill (copy+kernel)");
 		e->timing.fill_forward_launches += 1;
 		e->timing.cells_forward += cells;
-		if (resolve_forward(e, descs, desc_aln, alns, word, S, word_first, refill)) return -1;
+		if (resolve_forward(e, descs, desc_aln, alns, word, S, word_first, refill, &cm_mode)) return -1;
 		tr.lap("forward: resolve");
 		k = k_end;
 	}
@@ -940,16 +1078,16 @@ static int reverse_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			memset(&it, 0, sizeof(it));
 			it.qa.off = (int32_t)e->q_off[a.q]; it.qa.len = a.fwd.read + 1; it.qa.lp = lp_of(it.qa.len, a.word); it.qa.rev = 1;
 			it.ref_off = e->r_off[a.r]; it.ref_len = a.ref_len; it.cend = a.fwd.ref;
-			it.p0 = 0; it.p1 = a.fwd.ref + 1; it.warm = 0; it.term_a = a.fwd.score; it.cm_off = -1;
+			it.p0 = 0; it.p1 = a.fwd.ref + 1; it.warm = 0; it.term_a = a.fwd.score; it.cm_off = SSW_CM_NONE;
 			SswAlnDesc d;
 			memset(&d, 0, sizeof(d));
 			d.first_item = (int)items.size(); d.n_items = 1; d.half = 0; d.ref_len = it.p1; d.read_len = it.qa.len;
-			d.word = 1; d.limit = 0x7fffffff; d.mask_len = 0; d.cm_off = -1;
+			d.word = 1; d.limit = 0x7fffffff; d.mask_len = 0; d.cm_off = SSW_CM_NONE;
 			items.push_back(it);
 			descs.push_back(d);
 			desc_aln.push_back(keys[k].idx);
 		}
-		if (e->run_fill(items, inst, -1, 0, P, &e->timing.fill_reverse_ms)) return -1;
+		if (e->run_fill(items, inst, -1, 0, 0, P, &e->timing.fill_reverse_ms)) return -1;
 		e->timing.other_launches += 1;
 		if (merge(descs, desc_aln)) return -1;
 	}
@@ -967,7 +1105,7 @@ static int emul_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>&
 {
 	if (sel.empty()) return 0;
 	const size_t free_b = ssw_free_device_bytes();
-	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + e->d_emul.cap) / 2);
+	const size_t budget = std::max<size_t>((size_t)64 << 20, ssw_budget_share(free_b + e->d_emul.cap));
 	size_t k = 0;
 	while (k < sel.size()) {
 		std::vector<SswEmulTask> tasks;
@@ -1034,8 +1172,8 @@ static int emul_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>&
 static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, int64_t n_pairs,
                        ssw_batch_result* results, std::vector<int32_t>* redo)
 {
-	if (n_pairs != (int64_t)e->n_q * e->n_r || n_pairs < g_grid_min_pairs || n_pairs > 0x7fffffff) return 0;
-	if (P.flag != 0 || P.gap_open <= P.gap_extend || e->opt_chunk != 0) return 0;
+	if (n_pairs != (int64_t)e->n_q * e->n_r || n_pairs < e->opt.grid_min_pairs || n_pairs > 0x7fffffff) return 0;
+	if (P.flag != 0 || P.gap_open <= P.gap_extend || e->opt.chunk != 0) return 0;
 	if (!S.has_byte && !S.has_word) return 0;
 	const int word = S.has_byte ? 0 : 1;
 	const int limit = word ? S.limit_word : S.limit_byte;
@@ -1049,7 +1187,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		if (S.has_byte && S.has_word && (int64_t)len * std::max(S.max_mat, 0) >= 2 * (int64_t)S.limit_byte) return 0;   /* word-first prediction: general path */
 		qt[q].off = (int32_t)e->q_off[q]; qt[q].len = len; qt[q].lp = lp_of(len, word);
 		qt[q].mask_len = P.mask_len < 0 ? len / 2 : P.mask_len;
-		q_inst[q] = pick_inst(qt[q].lp);
+		q_inst[q] = pick_inst(qt[q].lp, e->opt.force_inst);
 		if (q_inst[q] < 0) return 0;
 	}
 	Trace tr;
@@ -1079,7 +1217,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 	if (e->d_out.ensure(sizeof(ssw_batch_result) * (size_t)n_pairs)) return -1;
 
 	const size_t free_b = ssw_free_device_bytes();
-	const size_t budget = std::max<size_t>((size_t)256 << 20, (free_b + e->d_colmax.cap + e->d_items.cap + e->d_alns.cap + e->d_res.cap) / 2);
+	const size_t budget = std::max<size_t>((size_t)256 << 20, ssw_budget_share(free_b + e->d_colmax.cap + e->d_items.cap + e->d_alns.cap + e->d_res.cap));
 	tr.lap("grid: tables");
 	size_t k = 0;
 	while (k < order.size()) {
@@ -1117,24 +1255,8 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		/* fill (items are already on the device) */
 		{
 			e->t_k.start(e->stream);
-			int rc = -1;
-			switch (inst) {
-			case 0: rc = launch_fill<8, 4>(e, (int)n_items, +1, 1, P); break;
-			case 1: rc = launch_fill<8, 5>(e, (int)n_items, +1, 1, P); break;
-			case 2: rc = launch_fill<8, 8>(e, (int)n_items, +1, 1, P); break;
-			case 3: rc = launch_fill<8, 10>(e, (int)n_items, +1, 1, P); break;
-			case 4: rc = launch_fill<8, 16>(e, (int)n_items, +1, 1, P); break;
-			case 5: rc = launch_fill<8, 20>(e, (int)n_items, +1, 1, P); break;
-			case 6: rc = launch_fill<16, 16>(e, (int)n_items, +1, 1, P); break;
-			case 7: rc = launch_fill<16, 20>(e, (int)n_items, +1, 1, P); break;
-			case 8: rc = launch_fill<32, 16>(e, (int)n_items, +1, 1, P); break;
-			case 9: rc = launch_fill<32, 20>(e, (int)n_items, +1, 1, P); break;
-			case 10: rc = launch_fill<32, 4>(e, (int)n_items, +1, 1, P); break;     /* 10..13: only through the "inst" option */
-			case 11: rc = launch_fill<32, 5>(e, (int)n_items, +1, 1, P); break;
-			case 12: rc = launch_fill<32, 8>(e, (int)n_items, +1, 1, P); break;
-			case 13: rc = launch_fill<32, 10>(e, (int)n_items, +1, 1, P); break;
-			default: break;
-			}
+			const FillPtrs fp = {e->d_items.as<SswItem>(), e->d_colmax.as<uint32_t>(), e->d_bests.as<SswItemBest>()};
+			const int rc = dispatch_fill(e, inst, fp, (int)n_items, +1, 1, 1, P);
 			if (rc) return rc < 0 ? rc : -1;
 			e->timing.fill_forward_ms += e->t_k.stop(e->stream);
 			e->timing.fill_forward_launches += 1;
@@ -1309,11 +1431,12 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 	/* ---- P3 ---- */
 	if (!tb.empty()) {
 		rc = ssw_traceback_run(e->stream, e->side, tb, e->d_q.as<int8_t>(), e->d_r.as<int8_t>(), e->d_mat.as<int8_t>(), P.n,
-		                       P.gap_open, P.gap_extend, &e->d_tb, &e->timing.traceback_ms, &e->timing.other_launches,
+		                       P.gap_open, P.gap_extend, &e->d_tb, &e->timing.traceback_ms, &e->timing.other_launches, e->opt.tb_maxbw,
 		                       [&](size_t i, const uint32_t* words, int32_t len, int failed) -> int {
 			ssw_batch_result& r = results[tb_pair[i]];
 			if (failed) { r.flag = 1; return 0; }                           /* ssw.c:968 */
 			if (!cigar_pool || *pool_used + len > pool_cap) { fprintf(stderr, "[libssw-b200] CIGAR pool too small\n"); return -1; }
+			if (*pool_used + len > 0x7fffffff) { fprintf(stderr, "[libssw-b200] more than 2^31 CIGAR words in one batch: split the batch\n"); return -1; }
 			r.cigar_off = (int32_t)*pool_used; r.cigar_len = len;
 			memcpy(cigar_pool + *pool_used, words, sizeof(uint32_t) * (size_t)len);
 			*pool_used += len;
@@ -1325,12 +1448,13 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 	return 0;
 }
 
-extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
-                                int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
-                                ssw_batch_result* results,
-                                uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
+static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
+                             int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                             ssw_batch_result* results,
+                             uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
 {
 	if (!e || !params || !params->mat || n_pairs < 0 || (n_pairs && !results)) return -1;
+	if (n_pairs > 0 && (e->n_q <= 0 || e->n_r <= 0)) { fprintf(stderr, "[libssw-b200] ssw_engine_align: no resident sequences\n"); return -1; }
 	const ssw_batch_params& P = *params;
 	if (P.n < 1 || P.n > 64) { fprintf(stderr, "[libssw-b200] alphabet size %d not supported (1..64)\n", P.n); return -1; }
 	if ((pair_query == nullptr) != (pair_ref == nullptr)) return -1;
@@ -1362,11 +1486,11 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 	 * the fills of the others (config 5: 329 -> 288 ms with three slices). */
 	{
 		int slices = 1;
-		if (!e->is_kid && g_slices != 1 && (P.flag & 7) != 0 && P.gap_open > P.gap_extend) {
+		if (!e->is_kid && e->opt.slices != 1 && (P.flag & 7) != 0 && P.gap_open > P.gap_extend) {
 			int64_t qsum = 0;
 			const int64_t probe = std::min<int64_t>(n_pairs, 64);
 			for (int64_t p = 0; p < probe; ++p) { const int32_t q = pair_query ? pair_query[p] : (int32_t)(p / e->n_r); if (q >= 0 && q < e->n_q) qsum += e->q_off[q + 1] - e->q_off[q]; }
-			if (g_slices > 1) slices = g_slices;
+			if (e->opt.slices > 1) slices = e->opt.slices;
 			else if (n_pairs >= 96 && qsum / probe >= 2000) slices = 3;
 			slices = (int)std::min<int64_t>(slices, n_pairs);
 		}
@@ -1398,7 +1522,7 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 				kid->n_q = e->n_q; kid->n_r = e->n_r; kid->q_off = e->q_off; kid->r_off = e->r_off; kid->r_len = e->r_len;
 				kid->padded_n = e->padded_n; kid->from_text = true;     /* no host copy: the padded references are the parent's */
 				kid->d_q.borrow(e->d_q); kid->d_r.borrow(e->d_r);
-				kid->opt_chunk = e->opt_chunk; kid->opt_small_chunk = e->opt_small_chunk;
+				kid->opt = e->opt;
 			}
 			auto work = [&](int k) {
 				Slice& s = sl[k];
@@ -1421,6 +1545,7 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 				if (s.rc) return s.rc;
 				if (s.used > 0) {
 					if (!cigar_pool || *pool_used + s.used > pool_cap) { fprintf(stderr, "[libssw-b200] CIGAR pool too small\n"); return -1; }
+					if (*pool_used + s.used > 0x7fffffff) { fprintf(stderr, "[libssw-b200] more than 2^31 CIGAR words in one batch: split the batch\n"); return -1; }
 					memcpy(cigar_pool + *pool_used, s.pool.get(), sizeof(uint32_t) * (size_t)s.used);
 					for (int64_t p = s.lo; p < s.hi; ++p) if (results[p].cigar_off >= 0) results[p].cigar_off += (int32_t)*pool_used;
 					*pool_used += s.used;
@@ -1456,4 +1581,15 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 	}
 	e->timing.total_ms = e->t_total.stop(e->stream);
 	return 0;
+}
+
+extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
+                                int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                                ssw_batch_result* results,
+                                uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
+{
+	/* nothing may unwind through the C ABI (std::bad_alloc from the planners' vectors, std::length_error, ...) */
+	try { return engine_align_impl(e, params, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_cap, pool_used); }
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_align: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
 }

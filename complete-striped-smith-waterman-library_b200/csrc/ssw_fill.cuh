@@ -279,7 +279,13 @@ __device__ static __forceinline__ void ssw_reduce_best(const SswLaneBest& lb, in
 #ifndef SSW_FILL_MINB
 #define SSW_FILL_MINB 4                     /* minimum resident CTAs per SM asked of ptxas: 128 registers; 16 warps/SM measured 3 % faster than 12 */
 #endif
-template <int G, int R, int DIR, bool WRITE_CM, bool TERM>
+/* CM: what the forward pass records of the column maxima (the reference's maxColumn[], ssw.c:338/:540)
+ *   0  nothing (reverse pass)
+ *   1  every column: one packed word per reference column (short references, the re-fill items of mode 2)
+ *   2  one packed word per block of SSW_CM_BLOCK columns.  The second-best scan (ssw.c:368-381) needs single columns
+ *      only in the <= 2 blocks cut by the mask window and in the block that holds the winner; ssw_resolve.cuh
+ *      re-fills those three blocks per alignment with mode 1.  Chunks start at multiples of SSW_CM_BLOCK. */
+template <int G, int R, int DIR, int CM, bool TERM>
 __global__ void __launch_bounds__(SSW_FILL_THREADS, SSW_FILL_MINB)
 ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
@@ -307,7 +313,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	if (live) it = items[item_idx];
 	else {
 		it.qa.off = it.qb.off = 0; it.qa.len = it.qb.len = 0; it.qa.lp = it.qb.lp = 0; it.qa.rev = it.qb.rev = 0;
-		it.ref_off = SSW_REF_PAD; it.ref_len = 0; it.cend = 0; it.p0 = it.p1 = 0; it.warm = 0; it.term_a = -1; it.cm_off = -1;
+		it.ref_off = SSW_REF_PAD; it.ref_len = 0; it.cend = 0; it.p0 = it.p1 = 0; it.warm = 0; it.term_a = -1; it.cm_off = SSW_CM_NONE;
 	}
 
 	if (share) {
@@ -322,7 +328,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	/* ---- sweep ---- */
 	const uint8_t* rp = reinterpret_cast<const uint8_t*>(refs) + it.ref_off;   /* reference column 0 */
 	const uint32_t negO = pack2(-gapO, -gapO), negE = pack2(-gapE, -gapE);
-	int sL = (it.p0 - it.warm - (G - 1)) & ~3;          /* scan position of the group's last lane, multiple of 4 */
+	int sL = (it.p0 - it.warm - (G - 1)) & (CM == 2 ? ~7 : ~3);   /* scan position of the group's last lane, multiple of 4 (block mode: of 8) */
 	constexpr int U = 8;                                /* scan positions per loop body */
 	int n_body = live && it.p1 > sL ? (it.p1 - sL + U - 1) / U : 0;
 #pragma unroll
@@ -351,6 +357,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
 	SswSnap<R> snap;
 	ssw_snap_pin<R>(snap);
+	uint32_t blk_acc = 0;                               /* CM == 2: running maximum of the current block (last lane) */
 
 	for (int body = 0; body < n_body; ++body) {
 		uint32_t cmv[U];
@@ -382,12 +389,31 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, it.p0, it.p1);
 		}
 
-		if (WRITE_CM) {
-			if (t == G - 1 && it.cm_off >= 0) {
+		if (CM == 1) {
+			if (t == G - 1 && it.cm_off != SSW_CM_NONE) {
 #pragma unroll
 				for (int q = 0; q < U; q += 4)
 					if (sL + q >= it.p0 && sL + q < it.p1)
 						*reinterpret_cast<uint4*>(colmax + it.cm_off + sL + q) = make_uint4(cmv[q], cmv[q + 1], cmv[q + 2], cmv[q + 3]);
+			}
+		}
+		if (CM == 2) {
+			/* p0 and sL are multiples of 8 here, so a body lies entirely before p0 or not at all; only the last body of the
+			 * reference can be cut by p1 (columns behind the reference must not count: E decays into the null pad) */
+			if (t == G - 1 && it.cm_off != SSW_CM_NONE && sL >= it.p0 && sL < it.p1) {
+				if (sL + U <= it.p1) {
+					blk_acc = __vimax3_s16x2(blk_acc, cmv[0], cmv[1]);
+					blk_acc = __vimax3_s16x2(blk_acc, cmv[2], cmv[3]);
+					blk_acc = __vimax3_s16x2(blk_acc, cmv[4], cmv[5]);
+					blk_acc = __vimax3_s16x2(blk_acc, cmv[6], cmv[7]);
+				} else {
+#pragma unroll
+					for (int j = 0; j < U; ++j) if (sL + j < it.p1) blk_acc = __vmaxs2(blk_acc, cmv[j]);
+				}
+				if (((sL + U) & (SSW_CM_BLOCK - 1)) == 0 || sL + U >= it.p1) {
+					colmax[it.cm_off + (sL / SSW_CM_BLOCK)] = blk_acc;
+					blk_acc = 0;
+				}
 			}
 		}
 		if (TERM) {
@@ -446,7 +472,7 @@ struct SswStripTask {
 	int32_t p1;            /* scan range [0, p1) */
 	int32_t term_a;        /* reverse pass: terminate score, else -1 */
 	int32_t n_strips, n_super;
-	int64_t cm_off;        /* column maxima written by the last strip (forward pass), -1: none */
+	int64_t cm_off;        /* column maxima written by the last strip (forward pass), SSW_CM_NONE: none */
 	int64_t bnd_off;       /* boundary arrays: 2 (strip parity) x 3 (H, F, C) x bnd_len words */
 	int32_t bnd_len;       /* words per boundary array: multiple of 4, >= p1 + 2*SSW_STRIP_BPAD + 8 */
 	int32_t first_best;    /* record of (strip s, super-block b) = first_best + s * n_super + b */
@@ -658,7 +684,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 							*reinterpret_cast<uint4*>(bout + g) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
 							*reinterpret_cast<uint4*>(bout + T.bnd_len + g) = make_uint4(fv[0], fv[1], fv[2], fv[3]);
 							*reinterpret_cast<uint4*>(bout + 2 * T.bnd_len + g) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
-						} else if (T.cm_off >= 0 && g < T.p1) {
+						} else if (T.cm_off != SSW_CM_NONE && g < T.p1) {
 							*reinterpret_cast<uint4*>(colmax + T.cm_off + g) = make_uint4(cmv[0], cmv[1], cmv[2], cmv[3]);
 						}
 					}

@@ -47,12 +47,12 @@ ssw_grid_plan_kernel(SswGridArgs A, const int2* __restrict__ qp, const SswGridQ*
 	if (pr.y >= 0) { qb = qt[pr.y]; it.qb.off = qb.off; it.qb.len = qb.len; it.qb.lp = qb.lp; }
 	it.ref_off = ref_off[r]; it.ref_len = ref_len[r]; it.cend = 0;
 	it.p0 = 0; it.p1 = live ? ref_len[r] : 0; it.warm = 0; it.term_a = -1;
-	it.cm_off = live ? (int64_t)pi * A.cm_words_per_qp + cm_prefix[r] : -1;
+	it.cm_off = live ? (int64_t)pi * A.cm_words_per_qp + cm_prefix[r] : SSW_CM_NONE;
 	items[idx] = it;
 	if (live) {
 		SswAlnDesc d;
 		d.first_item = (int32_t)idx; d.n_items = 1; d.half = 0; d.ref_len = it.ref_len; d.read_len = qa.len;
-		d.word = A.word; d.limit = A.limit; d.mask_len = qa.mask_len; d.cm_off = it.cm_off; d.scan_all = 0; d.pad_ = 0;
+		d.word = A.word; d.limit = A.limit; d.mask_len = qa.mask_len; d.cm_off = it.cm_off; d.scan_all = 0; d.warm = 0;
 		const int64_t di = ((int64_t)pi * A.n_r + r) * 2;
 		descs[di] = d;
 		d.half = 1; d.read_len = qb.len; d.mask_len = qb.mask_len;

@@ -15,6 +15,31 @@
  * this changed (cudaMemGetInfo costs milliseconds while a monitoring tool polls the driver) */
 inline std::atomic<unsigned long long>& ssw_alloc_epoch() { static std::atomic<unsigned long long> n{1}; return n; }
 
+/* engines alive in this process: every planner may claim 1 / (engines + 1) of the free device memory for its scratch, so
+ * that several engines on one device (helper engines of a sliced batch, the pool behind ssw_align, user-made ones) cannot
+ * claim the same half twice */
+inline std::atomic<int>& ssw_live_engines() { static std::atomic<int> n{0}; return n; }
+inline size_t ssw_budget_share(size_t bytes) { const int n = ssw_live_engines().load(); return bytes / (size_t)((n < 1 ? 1 : n) + 1); }
+
+/* 64-bit content hash (four interleaved multiply-xor lanes over 8-byte words): the resident-reference cache of ssw_align */
+inline uint64_t ssw_hash_bytes(const void* data, size_t len)
+{
+	const unsigned char* p = (const unsigned char*)data;
+	uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0x27D4EB2F165667C5ull};
+	size_t i = 0;
+	for (; i + 32 <= len; i += 32) {
+		uint64_t w[4];
+		memcpy(w, p + i, 32);
+		for (int k = 0; k < 4; ++k) { h[k] = (h[k] ^ w[k]) * 0x100000001B3ull; h[k] ^= h[k] >> 29; }
+	}
+	uint64_t tail[4] = {0, 0, 0, 0};
+	memcpy(tail, p + i, len - i);
+	for (int k = 0; k < 4; ++k) { h[k] = (h[k] ^ tail[k]) * 0x100000001B3ull; h[k] ^= h[k] >> 29; }
+	uint64_t r = (uint64_t)len;
+	for (int k = 0; k < 4; ++k) { r = (r ^ h[k]) * 0x9E3779B97F4A7C15ull; r ^= r >> 32; }
+	return r;
+}
+
 /* grow-only device buffer */
 struct SswDevBuf {
 	void* p = nullptr;
@@ -128,6 +153,11 @@ struct SswStagedD2H {
 		for (int i = 0; i < 2; ++i) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); pin[i] = nullptr; ev[i] = nullptr; }
 	}
 };
+
+/* internal entry points shared by ssw_engine.cu and ssw_capi.cu (not part of the public headers) */
+struct ssw_engine;
+extern "C" int ssw_engine_set_pair(ssw_engine* e, const int8_t* read, int32_t readLen, const int8_t* ref, int32_t refLen);
+int ssw_default_engines_option(const char* name, int64_t value);     /* ssw_engine_set_option(NULL, ...): the engines behind ssw_align */
 
 /* CUDA-event stopwatch on one stream */
 struct SswTimer {

@@ -258,7 +258,6 @@ __device__ static __forceinline__ void ssw_tb_row_group(int i, int j0, int beg, 
  * DRAM latency per step because every step moves up one band row.
  */
 #define SSW_TBP_MAXBW 990
-static int g_ssw_tb_maxbw = SSW_TBP_MAXBW;           /* "tb_maxbw" option: bands above this use the global-memory kernel (tests: 0) */
 
 __global__ void __launch_bounds__(SSW_TB_THREADS)
 ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
@@ -498,6 +497,7 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
                              std::vector<SswTbTask>& tasks,
                              const int8_t* d_q, const int8_t* d_r, const int8_t* d_mat, int n, int gapO, int gapE,
                              SswDevBuf* scratch, float* ms_acc, int64_t* launches,
+                             int tb_maxbw /* "tb_maxbw" option: bands above this use the global-memory kernel (tests: 0) */,
                              const std::function<int(size_t, const uint32_t*, int32_t, int)>& emit)
 {
 	std::vector<size_t> active(tasks.size());
@@ -510,8 +510,8 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 	}
 	const size_t free_b = ssw_free_device_bytes();
 	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + scratch->cap) / 2);
-	auto ring_of = [](const SswTbTask& t) -> int {          /* 0: single-warp kernel with global row buffers */
-		if (t.bw > g_ssw_tb_maxbw) return 0;
+	auto ring_of = [tb_maxbw](const SswTbTask& t) -> int {          /* 0: single-warp kernel with global row buffers */
+		if (t.bw > tb_maxbw) return 0;
 		int r = 256;
 		while (r < 2 * (4 * t.bw) + 66 && r < 2048) r <<= 1;    /* room for two in-kernel doublings */
 		while (r < 2 * t.bw + 66) r <<= 1;

@@ -92,7 +92,8 @@ int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 /*
  * Convenience: set_sequences + align + conversion to heap s_align records
  * (each to be released with align_destroy; NULL where ssw_align would return NULL).
- * e == NULL selects the process-wide engine that serves ssw_align (created on first use, calls serialised).
+ * e == NULL draws an engine from the pool that also serves ssw_align (engines are created on demand, up to
+ * SSW_B200_ENGINES, default 8; concurrent callers run side by side, each on its own engine and stream).
  */
 int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
                     int32_t n_queries, const int8_t* queries, const int64_t* query_off,
@@ -122,15 +123,20 @@ typedef struct {
 int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t);
 
 /*
- * Tuning knobs for tests and measurements; none of them changes a result.  Unknown names return -1.
+ * Tuning knobs for tests and measurements; none of them changes a result.  Unknown names return -1.  Every engine has
+ * its own set; e == NULL addresses the engines behind ssw_align / ssw_align_batch(NULL, ...) (present and future).
  *   "chunk"         reference chunk length in columns of the fill kernel (0 = automatic)
  *   "small_chunk"   the same for launches too small to fill the device (0 = automatic)
+ *   "cm_block"      column maxima of the forward fill: -1 automatic, 0 one word per column, 1 one word per 64 columns
+ *                   (+ re-fill of the blocks whose single columns matter) wherever the reference can be chunked
+ *   "cm_budget_mb"  cap of the column-maximum scratch per launch in MiB (0 = a share of the free device memory)
  *   "inst"          force forward kernel instance i (rows-per-lane / lanes-per-group table of the engine; -1 = automatic)
- *   "latency_cols"  passes over at most this many reference columns use the 32-lane instances (0 = never; process-wide)
- *   "parts"         CTAs per task of the strip-pipelined kernel: 0 automatic, 1 never split, 2 / 4 forced (process-wide)
- *   "super"         columns per super-block of the strip-pipelined kernel (process-wide)
- *   "grid_min"      smallest full score-only grid that is planned on the device (process-wide)
- *   "tb_maxbw"      widest band handled by the shared-memory traceback kernel (process-wide)
+ *   "latency_cols"  passes over at most this many reference columns use the 32-lane instances (0 = never)
+ *   "parts"         CTAs per task of the strip-pipelined kernel: 0 automatic, 1 never split, 2 / 4 forced
+ *   "super"         columns per super-block of the strip-pipelined kernel
+ *   "slices"        long-read CIGAR batches cut into slices on helper engines: 0 automatic, 1 never, 2 / 3 forced
+ *   "grid_min"      smallest full score-only grid that is planned on the device
+ *   "tb_maxbw"      widest band handled by the shared-memory traceback kernel
  */
 int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value);
 

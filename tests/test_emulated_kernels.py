@@ -48,12 +48,14 @@ def test_emulated_goldens(emu, capfd):
 
 
 def _latency_instances(on):
-    """Small passes use the 32-lane kernel instances ("latency_cols" option, process-wide); off = the layouts a large
-    batch gets, so that the small CPU cases cover both families."""
-    L = _pkg()
-    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
-    eng.set_option("latency_cols", (1 << 20) if on else 0)
-    eng.close()
+    """Small passes use the 32-lane kernel instances ("latency_cols" option, here set on the engines behind ssw_align:
+    engine NULL); off = the layouts a large batch gets, so that the small CPU cases cover both families."""
+    import ctypes as ct
+    lib = ct.CDLL(os.path.join(EMU_DIR, "libssw_emu.so"))
+    lib.ssw_engine_set_option.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_int64]
+    lib.ssw_engine_set_option.restype = ct.c_int
+    assert lib.ssw_engine_set_option(None, b"latency_cols", (1 << 20) if on else 0) == 0
+    assert lib.ssw_engine_set_option(None, b"no such option", 1) != 0
 
 
 @pytest.mark.parametrize("latency", [True, False])
@@ -77,6 +79,7 @@ def test_emulated_chunked_reference(oracle, capfd):
     subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
     eng.set_option("chunk", 64)
     rng = np.random.default_rng(99)
     mat = C.dna_matrix(2, 2)
@@ -103,6 +106,7 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
     subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
     eng.set_option("super", 256)
     rng = np.random.default_rng(515)
     mat = C.dna_matrix(2, 2)
@@ -157,6 +161,7 @@ def test_emulated_batch_grid_mixed_lengths(oracle, capfd):
     subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
     rng = np.random.default_rng(2024)
     mat = C.dna_matrix(2, 2)
     refs = [rng.integers(0, 4, size=n).astype(np.int8) for n in (300, 517, 90)]
@@ -206,6 +211,7 @@ def test_emulated_device_planned_grid(oracle, capfd):
     subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
     eng.set_option("grid_min", 1)
     rng = np.random.default_rng(31)
     mat = C.dna_matrix(2, 2)
@@ -246,6 +252,7 @@ def test_emulated_wide_bands_multi_tile(oracle, capfd):
     subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
     rng = np.random.default_rng(2718)
     mat = C.dna_matrix(2, 2)
     ref = rng.integers(0, 4, size=1600).astype(np.int8)
@@ -277,6 +284,7 @@ def test_emulated_text_sequences(oracle, capfd):
     subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
     rng = np.random.default_rng(4242)
     letters = np.frombuffer(b"ACGTacgtNnUuRY-", dtype=np.uint8)
     weights = np.array([20, 20, 20, 20, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1], dtype=float)
@@ -326,6 +334,7 @@ def test_emulated_align_batch_c_entry(oracle, capfd):
     subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
     lib = eng.lib
     rng = np.random.default_rng(3)
     ref = rng.integers(0, 4, size=400, dtype=np.int8)
@@ -395,3 +404,64 @@ def test_reference_c_consumers_unmodified_on_emulator_build(tmp_path):
         assert got == run["stdout"], (run["exe"], run["args"])
         n += 1
     assert n >= 8
+
+
+def test_emulated_block_column_maxima(capfd):
+    """Block-maximum mode of the forward fill (one word per 64 columns + re-fill of the three blocks per alignment whose single
+    columns matter) against the one-word-per-column mode and the compiled reference / oracle: second-best score and position
+    with the mask window at the start, in the middle, at the end of the reference, repeats (ties broken by the first column),
+    window edges on and off block boundaries, several chunk lengths."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
+    eng.set_option("latency_cols", 0)
+    rng = np.random.default_rng(2024)
+    mat = C.dna_matrix(2, 2)
+    motif = rng.integers(0, 4, size=48).astype(np.int8)
+    ref = rng.integers(0, 4, size=1700).astype(np.int8)
+    for at in (0, 130, 333, 640, 704, 1011, 1652):             # the same motif many times: equal second-best candidates
+        ref[at: at + 48] = motif
+    ref[400:430] = motif[:30]                                   # a weaker copy
+    reads = [motif.copy(), motif[4:44].copy(), np.concatenate([motif[:24], rng.integers(0, 4, size=6).astype(np.int8), motif[24:]])]
+    reads += [C.mutate_read(rng, ref, int(rng.integers(0, 1600)), int(rng.integers(25, 60)), 0.08, 0.02, 0.02) for _ in range(9)]
+    reads.append(rng.integers(0, 4, size=40).astype(np.int8))
+    eng.set_sequences(reads, [ref])
+    n = len(reads)
+    exp, exp_pool, _, _, _ = C.cpu_batch(reads, [ref], np.arange(n), np.zeros(n), mat, 5, 3, 1, flag=0, mask_len=20, score_size=2,
+                                        threads=4)
+    assert len(set(int(x) for x in exp["score2"])) > 3 and int((exp["score2"] > 0).sum()) >= n - 2
+    for mask_len in (20, 15, 64, 100):
+        exp, exp_pool, _, _, _ = C.cpu_batch(reads, [ref], np.arange(n), np.zeros(n), mat, 5, 3, 1, flag=0, mask_len=mask_len,
+                                            score_size=2, threads=4)
+        for cm_block, chunk in ((1, 0), (1, 64), (1, 128), (1, 320), (0, 64)):
+            eng.set_option("cm_block", cm_block)
+            eng.set_option("chunk", chunk)
+            res, pool = eng.align(mat, 5, 3, 1, flag=0, mask_len=mask_len, score_size=2)
+            bad = C.compare_records(res, pool, exp, exp_pool)
+            assert bad == [], (mask_len, cm_block, chunk, bad, [(res[i], exp[i]) for i in bad[:2]])
+    eng.set_option("cm_block", -1)
+    eng.set_option("chunk", 0)
+    eng.close()
+
+
+def test_emulated_resident_reference_cache(emu, oracle, capfd):
+    """ssw_align re-uses the resident reference while length and content hash are unchanged; rewriting the caller's buffer in
+    place (same pointer, same length) must be noticed.  Also: alphabet changes between calls (the null letter of the pads)."""
+    rng = np.random.default_rng(77)
+    mat = C.dna_matrix(2, 2)
+    ref = rng.integers(0, 4, size=900, dtype=np.int8)
+    reads = [C.mutate_read(rng, ref, int(rng.integers(0, 800)), 40, 0.05, 0.01, 0.01) for _ in range(3)]
+    for rnd in range(3):
+        for q in reads:
+            kw = dict(read=q, ref=ref, mat=mat, n=5, gapO=3, gapE=1, flag=0x0f, filters=0, filterd=32767, maskLen=20, score_size=2)
+            assert C.diff_results(emu.align(**kw), oracle.align(**kw)) == []
+        ref[:] = np.roll(ref, 131)
+        ref[int(rng.integers(0, 900))] ^= 1
+    # same reference bytes, other alphabet size: the pads must be rewritten with the new null letter
+    mat8 = np.zeros((8, 8), dtype=np.int8) - 3
+    np.fill_diagonal(mat8, 4)
+    kw = dict(read=reads[0], ref=ref, mat=mat8.reshape(-1).copy(), n=8, gapO=5, gapE=2, flag=8, filters=0, filterd=0, maskLen=20, score_size=2)
+    assert C.diff_results(emu.align(**kw), oracle.align(**kw)) == []
+    kw = dict(read=reads[1], ref=ref, mat=mat, n=5, gapO=3, gapE=1, flag=8, filters=0, filterd=0, maskLen=20, score_size=2)
+    assert C.diff_results(emu.align(**kw), oracle.align(**kw)) == []

@@ -353,14 +353,16 @@ def test_cpp_wrapper_matches_reference_wrapper(tmp_path):
 
 
 def test_concurrent_callers(ours, checker, capfd):
-    """ssw_align is called from several host threads at once (the reference is re-entrant, SURVEY 8(b) Threading; ours
-    serialises the calls on the process-wide engine): every caller gets its own, correct record."""
+    """ssw_align is called from several host threads at once (the reference is re-entrant, SURVEY 8(b) Threading): every
+    caller gets its own, correct record, and the calls really run side by side (engine pool: own stream and scratch per
+    call) -- eight threads finish the same calls faster than one thread does."""
+    import time
     from concurrent.futures import ThreadPoolExecutor
     rng = np.random.default_rng(31337)
     mat = C.dna_matrix(2, 2)
     cases = []
-    for _ in range(96):
-        ref = rng.integers(0, 4, size=int(rng.integers(200, 4000)), dtype=np.int8)
+    for _ in range(192):
+        ref = rng.integers(0, 4, size=int(rng.integers(20_000, 60_000)), dtype=np.int8)
         start = int(rng.integers(0, len(ref) - 120))
         q = C.mutate_read(rng, ref, start, int(rng.integers(30, 110)), 0.08, 0.02, 0.02)
         cases.append((q, ref, int(rng.choice([0, 1, 2, 8, 0x0f]))))
@@ -369,12 +371,38 @@ def test_concurrent_callers(ours, checker, capfd):
         q, ref, flag = c
         return ours.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, max(15, len(q) // 2), 2)
 
+    with ThreadPoolExecutor(8) as ex:                 # warm-up: creates the pool's engines and their scratch
+        list(ex.map(run, cases[:32]))
+    t0 = time.perf_counter()
+    serial = [run(c) for c in cases]
+    t_serial = time.perf_counter() - t0
+    t0 = time.perf_counter()
     with ThreadPoolExecutor(8) as ex:
         got = list(ex.map(run, cases))
-    for c, g in zip(cases, got):
+    t_conc = time.perf_counter() - t0
+    for c, g, s1 in zip(cases, got, serial):
         q, ref, flag = c
         exp = checker.align(q, ref, mat, 5, 3, 1, flag, 0, 32767, max(15, len(q) // 2), 2)
         assert C.diff_results(g, exp) == [], flag
+        assert C.diff_results(s1, exp) == [], flag
+    with capfd.disabled():
+        print("\n[concurrent callers] 192 ssw_align calls: one thread %.1f ms, eight threads %.1f ms" % (t_serial * 1e3, t_conc * 1e3))
+    assert t_conc < 0.8 * t_serial, (t_serial, t_conc)
+
+
+def test_resident_reference_is_reused_only_while_its_bytes_are_unchanged(ours, checker, capfd):
+    """ssw_align keeps the last reference resident (length + content hash) so that a loop of reads over one reference
+    (main.c:462-532) uploads it once; a caller that rewrites the buffer in place must still get answers for the new bytes."""
+    rng = np.random.default_rng(99)
+    mat = C.dna_matrix(2, 2)
+    ref = rng.integers(0, 4, size=50_000, dtype=np.int8)
+    reads = [C.mutate_read(rng, ref, int(rng.integers(0, 49_000)), 80, 0.05, 0.01, 0.01) for _ in range(6)]
+    for rnd in range(3):
+        for q in reads:
+            g = ours.align(q, ref, mat, 5, 3, 1, 0x0f, 0, 32767, 40, 2)
+            assert C.diff_results(g, checker.align(q, ref, mat, 5, 3, 1, 0x0f, 0, 32767, 40, 2)) == []
+        ref[:] = np.roll(ref, 7777)                    # same pointer, same length, different content
+        ref[int(rng.integers(0, 50_000))] ^= 1
 
 
 def test_text_sequences_on_device(engine, checker, capfd):

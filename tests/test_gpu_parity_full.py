@@ -4,12 +4,11 @@ cores of the GPU box:
   config 3: a fixed 2,000-read subsample of the 100,000-read set;
   config 4: a 200 x 1,000 sub-grid of the protein grid, word scores;
   config 5: 1,000 x 10 kbp long reads, flags 0x0f and 2, every field and every CIGAR word.
-The reference side is CPU-bound (~1e12 cells per case); each case checks its pairs in blocks until a time budget is
-used up, requires a minimum number checked, and records the coverage in gpurun_out/parity_full.json."""
+The reference side is CPU-bound (~1e12 cells per case, tens of seconds on the box's usable cores); EVERY pair of every case is
+checked (oracle/ssw_harness.c), the coverage is printed to stdout and recorded in gpurun_out/parity_full.json."""
 import json
 import os
 import time
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import pytest
@@ -19,8 +18,7 @@ from test_gpu_parity import FIELDS8, batch_dict, engine  # noqa: F401  (fixture)
 
 pytestmark = pytest.mark.gpu
 
-BUDGET_S = float(os.environ.get("SSW_FULL_PARITY_BUDGET", "75"))
-THREADS = max(1, (os.cpu_count() or 2) - 2)
+THREADS = C.effective_cores()[0]
 
 
 _cache = {}
@@ -45,27 +43,27 @@ def _record(name, info):
         json.dump(data, f, indent=1, sort_keys=True)
 
 
-def check_pairs(name, res, pool, pairs, ref_call, minimum):
-    """pairs: list of (result index, thunk args); ref_call(args) -> expected dict.  Blocks of THREADS*2 pairs."""
+_expected = {}
+
+
+def check_all(name, capfd, res, pool, queries, refs, pair_q, pair_r, mat, n, expect_key=None, **kw):
+    """EVERY pair is re-computed by the compiled reference on all usable host cores (pthread harness) and compared field by
+    field and CIGAR word by CIGAR word; the coverage goes to stdout (so that it lands in the driver's test log) and to
+    gpurun_out/parity_full.json."""
     t0 = time.time()
-    done = 0
-    bad = []
-    with ThreadPoolExecutor(THREADS) as ex:
-        step = THREADS * 2
-        for lo in range(0, len(pairs), step):
-            if done >= minimum and time.time() - t0 > BUDGET_S:
-                break
-            block = pairs[lo: lo + step]
-            for (idx, _), exp in zip(block, ex.map(ref_call, [a for _, a in block])):
-                d = C.diff_results(batch_dict(res, pool, idx), exp)
-                if d:
-                    bad.append((idx, d))
-            done += len(block)
-    _record(name, {"pairs_total": len(pairs), "pairs_checked": done, "mismatches": len(bad), "threads": THREADS,
-                   "seconds": round(time.time() - t0, 1)})
-    assert not bad, bad[:3]
-    assert done >= minimum
-    return done
+    if expect_key is None or expect_key not in _expected:
+        _expected[expect_key] = C.cpu_batch(queries, refs, pair_q, pair_r, mat, n, impl="reference", threads=THREADS, **kw)
+    exp, exp_pool, secs, cells, kind = _expected[expect_key]
+    if expect_key is None:
+        del _expected[None]
+    bad = C.compare_records(res, pool, exp, exp_pool)
+    info = {"pairs_total": int(len(pair_q)), "pairs_checked": int(len(exp)), "mismatches": len(bad), "threads": THREADS,
+            "seconds": round(time.time() - t0, 1), "checker": kind, "checker_gcups": round(cells / secs / 1e9, 1)}
+    _record(name, info)
+    with capfd.disabled():
+        print("\n[parity %s] %s" % (name, json.dumps(info)))
+    assert len(exp) == len(pair_q) == len(res)
+    assert bad == [], (bad[:3], [(res[i], exp[i]) for i in bad[:2]])
 
 
 @pytest.fixture(scope="module")
@@ -76,57 +74,62 @@ def ref_lib():
 
 
 @pytest.mark.parametrize("flag", [0x0f, 0])
-def test_config2_all_reads(engine, ref_lib, flag):
+def test_config2_all_reads(engine, ref_lib, flag, capfd):
     ref, reads = _workload(5_000_000, 1000, 150, 1001, 2002)
     mat = C.dna_matrix(2, 2)
     engine.set_sequences(reads, [ref])
     res, pool = engine.align(mat, 5, 3, 1, flag=flag, filters=0, filterd=32767, mask_len=75, score_size=2)
-    pairs = [(i, i) for i in range(len(reads))]
-    check_pairs("config2_flag%d" % flag, res, pool, pairs,
-                lambda i: ref_lib.align(reads[i], ref, mat, 5, 3, 1, flag, 0, 32767, 75, 2), minimum=256)
+    n = len(reads)
+    check_all("config2_flag%d" % flag, capfd, res, pool, reads, [ref], np.arange(n), np.zeros(n), mat, 5,
+              gapO=3, gapE=1, flag=flag, filters=0, filterd=32767, mask_len=75, score_size=2)
 
 
-def test_config3_subsample(engine, ref_lib):
-    """the first 2,000 reads of the 100,000-read set of config 3 (seed 3003; the generator is sequential)"""
+@pytest.mark.parametrize("mode", ["auto", "blocks_3_launches", "columns_3_launches"])
+def test_config3_subsample(engine, ref_lib, mode, capfd):
+    """the first 2,000 reads of the 100,000-read set of config 3 (seed 3003; the generator is sequential): in one launch
+    (automatic: block column maxima), and forced through >= 3 launches by a capped column-maximum budget in both storage
+    modes -- the multi-launch path the full 100,000-read batch takes."""
     ref, sub = _workload(5_000_000, 2000, 150, 1001, 3003)
     mat = C.dna_matrix(2, 2)
     engine.set_sequences(sub, [ref])
-    res, pool = engine.align(mat, 5, 3, 1, flag=0, mask_len=75, score_size=2)
-    pairs = [(i, i) for i in range(len(sub))]
-    check_pairs("config3_subsample", res, pool, pairs,
-                lambda i: ref_lib.align(sub[i], ref, mat, 5, 3, 1, 0, 0, 0, 75, 2), minimum=256)
+    if mode == "blocks_3_launches":
+        engine.set_option("cm_block", 1)
+        engine.set_option("cm_budget_mb", 110)           # 1,000 pair-tasks x 312 KB of block maxima = 312 MB
+    elif mode == "columns_3_launches":
+        engine.set_option("cm_block", 0)
+        engine.set_option("cm_budget_mb", 7000)          # 1,000 pair-tasks x 20 MB of column maxima = 20 GB
+    try:
+        res, pool = engine.align(mat, 5, 3, 1, flag=0, mask_len=75, score_size=2)
+        launches = engine.timing()["fill_forward_launches"]
+    finally:
+        engine.set_option("cm_block", -1)
+        engine.set_option("cm_budget_mb", 0)
+    if mode != "auto":
+        assert launches >= 4, launches                   # >= 3 byte-semantics launches + the word re-fill of the overflows
+    n = len(sub)
+    check_all("config3_subsample_" + mode, capfd, res, pool, sub, [ref], np.arange(n), np.zeros(n), mat, 5, expect_key="config3",
+              gapO=3, gapE=1, flag=0, filters=0, filterd=0, mask_len=75, score_size=2)
 
 
-def test_config4_subgrid(engine, ref_lib):
+def test_config4_subgrid(engine, ref_lib, capfd):
     """200 queries x 1,000 targets of the BLOSUM50 grid (seeds 4004 / 4005), word scores, through the grid path"""
-    rq, rt = np.random.default_rng(4004), np.random.default_rng(4005)
-    queries = [rq.integers(0, 20, size=300).astype(np.int8) for _ in range(200)]
-    targets = []
-    for t in range(1000):
-        s = rt.integers(0, 20, size=400).astype(np.int8)
-        if t % 10 == 0:
-            q = queries[int(rt.integers(0, len(queries)))]
-            a = int(rt.integers(0, 100))
-            seg = q[a: a + 200].copy()
-            m = rt.random(len(seg)) < 0.2
-            seg[m] = rt.integers(0, 20, size=int(m.sum()))
-            b = int(rt.integers(0, 200))
-            s[b: b + 200] = seg
-        targets.append(s)
+    W = C.config_workload(4, n_queries=200, n_targets=1000)
+    queries, targets = W["queries"], W["refs"]
     engine.set_sequences(queries, targets)
     res, pool = engine.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
-    pairs = [(q * 1000 + t, (q, t)) for q in range(200) for t in range(1000)]
-    check_pairs("config4_subgrid", res, pool, pairs,
-                lambda a: ref_lib.align(queries[a[0]], targets[a[1]], C.BLOSUM50, 24, 3, 1, 0, 0, 0, 150, 1), minimum=20_000)
+    pq = np.repeat(np.arange(200), 1000)
+    pr = np.tile(np.arange(1000), 200)
+    check_all("config4_subgrid", capfd, res, pool, queries, targets, pq, pr, C.BLOSUM50, 24,
+              gapO=3, gapE=1, flag=0, filters=0, filterd=0, mask_len=150, score_size=1)
 
 
 @pytest.mark.parametrize("flag", [0x0f, 2])
-def test_config5_all_long_reads(engine, ref_lib, flag):
+def test_config5_all_long_reads(engine, ref_lib, flag, capfd):
     ref, reads = _workload(100_000, 1000, 10_000, 5005, 5006, decoy_frac=0.0, p_sub=0.05, p_ins=0.02, p_del=0.02)
     mat = C.dna_matrix(2, 2)
     engine.set_sequences(reads, [ref])
     res, pool = engine.align(mat, 5, 3, 1, flag=flag, filters=0, filterd=32767, mask_len=5000, score_size=2)
     assert int((res["cigar_len"] > 0).sum()) == len(reads)
-    pairs = [(i, i) for i in range(len(reads))]
-    check_pairs("config5_flag%d" % flag, res, pool, pairs,
-                lambda i: ref_lib.align(reads[i], ref, mat, 5, 3, 1, flag, 0, 32767, 5000, 2), minimum=128)
+    n = len(reads)
+    check_all("config5_flag%d" % flag, capfd, res, pool, reads, [ref], np.arange(n), np.zeros(n), mat, 5,
+              gapO=3, gapE=1, flag=flag, filters=0, filterd=32767, mask_len=5000, score_size=2)
