@@ -116,7 +116,8 @@ struct ssw_engine {
 	bool is_kid = false;
 	SswOptions opt;
 	ssw_engine_timing timing;
-	SswTimer t_total, t_k;
+	SswTimer t_total;
+	SswLaps laps;                    /* per-phase kernel times, read once at the end of a call */
 
 	int upload_refs(int n);
 	int run_fill(const std::vector<SswItem>& items, int inst, int dir, int cm_mode, int share, const ssw_batch_params& P, float* ms_acc);
@@ -134,12 +135,12 @@ static int launch_fill(ssw_engine* e, const FillPtrs& fp, int n_items, int dir, 
 {
 	constexpr int GPW = 32 / G;
 	/* per-warp profiles (share == 0) can be large for big alphabets: use fewer warps per CTA then */
-	const size_t warp_smem = ssw_fill_smem_bytes<R>(P.n, 1);
+	const size_t warp_smem = ssw_fill_smem_bytes<R>(P.n, 1), warp_snap = ssw_snap_smem_bytes<R>(32);
 	int warps = SSW_FILL_WARPS;
-	if (!share) while (warps > 1 && warp_smem * warps > 200 * 1024) --warps;
+	if (!share) while (warps > 1 && (warp_smem + warp_snap) * warps > 200 * 1024) --warps;
 	const int per_cta = warps * GPW;
 	const int grid = (n_items + per_cta - 1) / per_cta;
-	const size_t smem = share ? warp_smem : warp_smem * warps;
+	const size_t smem = (share ? warp_smem : warp_smem * warps) + warp_snap * warps;       /* profile(s), then the best-cell snapshots */
 	if (smem > 220 * 1024) { fprintf(stderr, "[libssw-b200] alphabet of %d letters is too large for this query length\n", P.n); return -2; }
 	const SswItem* items = fp.items;
 	const int8_t* q = e->d_q.as<int8_t>();
@@ -195,11 +196,11 @@ int ssw_engine::run_fill(const std::vector<SswItem>& items, int inst, int dir, i
 	Trace tr;
 	SSW_CUDA_OK(cudaMemcpyAsync(d_items.p, items.data(), sizeof(SswItem) * items.size(), cudaMemcpyHostToDevice, stream));
 	tr.lap("  fill: items h2d");
-	t_k.start(stream);
+	laps.start(stream);
 	const FillPtrs fp = {d_items.as<SswItem>(), d_colmax.as<uint32_t>(), d_bests.as<SswItemBest>()};
 	const int rc = dispatch_fill(this, inst, fp, n_items, dir, cm_mode, share, P);
 	tr.lap("  fill: launch");
-	*ms_acc += t_k.stop(stream);
+	laps.stop(stream, ms_acc);
 	tr.lap("  fill: wait");
 	return rc;
 }
@@ -210,7 +211,7 @@ template <int G, int R>
 static int fill_occ_of(int n)
 {
 	int occ = 0;
-	const size_t smem = ssw_fill_smem_bytes<R>(n, 1);
+	const size_t smem = ssw_fill_smem_bytes<R>(n, 1) + ssw_snap_smem_bytes<R>(SSW_FILL_THREADS);
 	auto kern = ssw_fill_kernel<G, R, 1, 2, false>;
 	ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSW_FILL_THREADS, smem) != cudaSuccess) occ = 1;
@@ -537,7 +538,7 @@ static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool
 	if (e->d_alns.ensure(sizeof(SswAlnDesc) * descs.size())) return -1;
 	if (e->d_res.ensure(sizeof(SswFillResult) * descs.size())) return -1;
 	SSW_CUDA_OK(cudaMemcpyAsync(e->d_alns.p, descs.data(), sizeof(SswAlnDesc) * descs.size(), cudaMemcpyHostToDevice, e->stream));
-	e->t_k.start(e->stream);
+	e->laps.start(e->stream);
 	const int per = SSW_RESOLVE_THREADS / 32;
 	const dim3 grid(((int)descs.size() + per - 1) / per);
 	if (second && cm && cm->block) {
@@ -565,7 +566,7 @@ static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool
 		ssw_launch(ssw_resolve_kernel<false>, grid, dim3(SSW_RESOLVE_THREADS), 0, e->stream, (const SswAlnDesc*)e->d_alns.as<SswAlnDesc>(),
 		           (int)descs.size(), (const SswItemBest*)e->d_bests.as<SswItemBest>(), (const uint32_t*)nullptr, e->d_res.as<SswFillResult>());
 	SSW_CUDA_OK(cudaGetLastError());
-	e->timing.resolve_ms += e->t_k.stop(e->stream);
+	e->laps.stop(e->stream, &e->timing.resolve_ms);
 	e->timing.other_launches += 1;
 	SSW_CUDA_OK(cudaMemcpyAsync(res.data(), e->d_res.p, sizeof(SswFillResult) * descs.size(), cudaMemcpyDeviceToHost, e->stream));
 	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
@@ -623,7 +624,8 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 	constexpr int R = SSW_STRIP_R;
 	Trace tr;
 	const int rows_per_strip = 32 * R;
-	const size_t warp_smem = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t);
+	const size_t warp_smem = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t) + ssw_snap_smem_bytes<R>(32);      /* profile + best-cell snapshots of one warp */
+	const size_t warp_prof = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t);
 	/* one launch per distinct strip count (it fixes the CTA shape) */
 	std::vector<size_t> order(reqs.size());
 	for (size_t i = 0; i < reqs.size(); ++i) order[i] = i;
@@ -725,9 +727,9 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		gsync[0] = 0;
 		if (e->d_sync.ensure(sizeof(int) * gsync.size())) return -1;
 		SSW_CUDA_OK(cudaMemcpyAsync(e->d_sync.p, gsync.data(), sizeof(int) * gsync.size(), cudaMemcpyHostToDevice, e->stream));
-		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 4);
+		const size_t smem = (size_t)nw * warp_prof + sizeof(int) * (size_t)((n_strips + 2 + 3) / 4 * 4) + ssw_snap_smem_bytes<R>(nw * 32);
 		tr.lap("strips: h2d + memset");
-		e->t_k.start(e->stream);
+		e->laps.start(e->stream);
 #define SSW_STRIPS_GO(DIR, TERM, SPLIT)                                                                                 \
 		do {                                                                                                            \
 			auto kern = ssw_fill_strips_kernel<SSW_STRIP_R, DIR, TERM, SPLIT>;                                          \
@@ -741,7 +743,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		else SSW_STRIPS_GO(-1, true, false);
 #undef SSW_STRIPS_GO
 		SSW_CUDA_OK(cudaGetLastError());
-		*ms_acc += e->t_k.stop(e->stream);
+		e->laps.stop(e->stream, ms_acc);
 		if (dir > 0) e->timing.fill_forward_launches += 1; else e->timing.other_launches += 1;
 		tr.lap("strips: kernel");
 		const int rc = after(descs, desc_aln);
@@ -1140,16 +1142,15 @@ static int emul_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Aln>&
 		uint8_t* base = e->d_emul.as<uint8_t>();
 		SSW_CUDA_OK(cudaMemsetAsync(base + off_cm, 0, cm_elems * 2, e->stream));
 		SSW_CUDA_OK(cudaMemcpyAsync(base + off_tasks, tasks.data(), sizeof(SswEmulTask) * tasks.size(), cudaMemcpyHostToDevice, e->stream));
-		e->t_k.start(e->stream);
+		e->laps.start(e->stream);
 		ssw_launch(ssw_emul_kernel, dim3(((int)tasks.size() + SSW_EMUL_WARPS - 1) / SSW_EMUL_WARPS), dim3(SSW_EMUL_THREADS), 0, e->stream,
 		           (const SswEmulTask*)reinterpret_cast<SswEmulTask*>(base + off_tasks), (int)tasks.size(),
 		           (const int8_t*)e->d_q.as<int8_t>(), (const int8_t*)e->d_r.as<int8_t>(), (const int8_t*)e->d_mat.as<int8_t>(), (int)P.n,
 		           (int)P.gap_open, (int)P.gap_extend, reinterpret_cast<int32_t*>(base), reinterpret_cast<uint16_t*>(base + off_cm),
 		           reinterpret_cast<SswFillResult*>(base + off_res));
 		SSW_CUDA_OK(cudaGetLastError());
-		const float ms = e->t_k.stop(e->stream);
-		if (dir) { e->timing.fill_reverse_ms += ms; e->timing.other_launches += 1; }
-		else { e->timing.fill_forward_ms += ms; e->timing.fill_forward_launches += 1; }
+		e->laps.stop(e->stream, dir ? &e->timing.fill_reverse_ms : &e->timing.fill_forward_ms);
+		if (dir) e->timing.other_launches += 1; else e->timing.fill_forward_launches += 1;
 		std::vector<SswFillResult> res(tasks.size());
 		SSW_CUDA_OK(cudaMemcpyAsync(res.data(), base + off_res, sizeof(SswFillResult) * tasks.size(), cudaMemcpyDeviceToHost, e->stream));
 		SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
@@ -1244,25 +1245,25 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		if (e->d_res.ensure(sizeof(SswFillResult) * (size_t)n_desc)) return -1;
 		if (e->d_colmax.ensure((size_t)A.n_qp * (size_t)cm_per_qp * 4 + 64)) return -1;
 		SSW_CUDA_OK(cudaMemcpyAsync(gb + o_qp, qps.data(), sizeof(int2) * qps.size(), cudaMemcpyHostToDevice, e->stream));
-		e->t_k.start(e->stream);
+		e->laps.start(e->stream);
 		ssw_launch(ssw_grid_plan_kernel, dim3((unsigned)((n_items + 255) / 256)), dim3(256), 0, e->stream, A,
 		           (const int2*)reinterpret_cast<int2*>(gb + o_qp), (const SswGridQ*)reinterpret_cast<SswGridQ*>(gb + o_qt),
 		           (const int64_t*)reinterpret_cast<int64_t*>(gb + o_roff), (const int32_t*)reinterpret_cast<int32_t*>(gb + o_rlen),
 		           (const int64_t*)reinterpret_cast<int64_t*>(gb + o_cmp), e->d_items.as<SswItem>(), e->d_alns.as<SswAlnDesc>());
 		SSW_CUDA_OK(cudaGetLastError());
-		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		e->laps.stop(e->stream, &e->timing.resolve_ms);
 		e->timing.other_launches += 1;
 		/* fill (items are already on the device) */
 		{
-			e->t_k.start(e->stream);
+			e->laps.start(e->stream);
 			const FillPtrs fp = {e->d_items.as<SswItem>(), e->d_colmax.as<uint32_t>(), e->d_bests.as<SswItemBest>()};
 			const int rc = dispatch_fill(e, inst, fp, (int)n_items, +1, 1, 1, P);
 			if (rc) return rc < 0 ? rc : -1;
-			e->timing.fill_forward_ms += e->t_k.stop(e->stream);
+			e->laps.stop(e->stream, &e->timing.fill_forward_ms);
 			e->timing.fill_forward_launches += 1;
 			e->timing.cells_forward += (int64_t)A.n_qp * (cm_per_qp) * kInst[inst].G * kInst[inst].R * 2;
 		}
-		e->t_k.start(e->stream);
+		e->laps.start(e->stream);
 		{
 			const int per = SSW_RESOLVE_THREADS / 32;
 			ssw_launch(ssw_resolve_kernel<true>, dim3((unsigned)((n_desc + per - 1) / per)), dim3(SSW_RESOLVE_THREADS), 0, e->stream,
@@ -1274,7 +1275,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 			           reinterpret_cast<int32_t*>(gb + o_list), reinterpret_cast<int32_t*>(gb + o_cnt), redo_cap);
 			SSW_CUDA_OK(cudaGetLastError());
 		}
-		e->timing.resolve_ms += e->t_k.stop(e->stream);
+		e->laps.stop(e->stream, &e->timing.resolve_ms);
 		e->timing.other_launches += 2;
 		tr.lap("grid: launch group");
 	}
@@ -1463,6 +1464,7 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 	*pool_used = 0;
 	SSW_CUDA_OK(cudaSetDevice(e->device));
 	memset(&e->timing, 0, sizeof(e->timing));
+	e->laps.laps.clear(); e->laps.used = 0;            /* a call that failed half-way leaves its laps behind */
 	if (n_pairs == 0) return 0;
 	e->t_total.start(e->stream);
 
@@ -1557,6 +1559,7 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 				e->timing.cells_forward += t.cells_forward; e->timing.byte_overflows += t.byte_overflows;
 			}
 			e->timing.total_ms = e->t_total.stop(e->stream);
+			e->laps.collect();
 			return 0;
 		}
 	}
@@ -1580,6 +1583,7 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 		if (rc) return rc;
 	}
 	e->timing.total_ms = e->t_total.stop(e->stream);
+	e->laps.collect();
 	return 0;
 }
 

@@ -96,7 +96,7 @@ __device__ static __forceinline__ uint32_t ssw_lds32(ssw_saddr a)
 
 /* shared-memory bytes for an alphabet of n letters */
 template <int R>
-static inline size_t ssw_fill_smem_bytes(int n, int warps = SSW_FILL_WARPS) { return (size_t)warps * (size_t)(n + 1) * 32 * R * sizeof(uint32_t); }
+static inline size_t ssw_fill_smem_bytes(int n, int warps = SSW_FILL_WARPS) { return (size_t)warps * (size_t)(n + 1) * 32 * R * sizeof(uint32_t); }   /* profiles only; the snapshot area (ssw_snap_smem_bytes) comes on top */
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* shared device code                                                                                          */
@@ -200,37 +200,46 @@ struct SswLaneBest {
 	uint32_t best;
 	int pos0, pos1, row0, row1;
 };
+/* The snapshot lives in shared memory, [thread][half][group of four rows] as 128-bit words with one word of padding per
+ * thread (2Q+1 words: conflict-free 128-bit stores for every Q in use, addresses = one base register + immediates):
+ * an event is (R+3)/4 vector stores per half.  With BLOSUM50 and 3/1 gaps, or along the true diagonal of a long read, the
+ * running maximum grows with every column and some lane of a warp has an event on almost every step; a snapshot kept in
+ * registers made the event 2R register moves (21 % of all executed instructions of the config-4 kernel in round 1,
+ * profiles/ncu_fill_cfg4_r1.txt). */
 template <int R>
 struct SswSnap {
-	uint32_t w[2][R + (4 - R % 4) % 4];
+	uint4* base;        /* this thread's slots: (h, q) is base[h * Q + q] */
+	static constexpr int Q = (R + 3) / 4;
 };
 template <int R>
-__device__ static __forceinline__ void ssw_snap_pin(SswSnap<R>& sn)
+static inline size_t ssw_snap_smem_bytes(int threads) { return (size_t)(2 * ((R + 3) / 4) + 1) * (size_t)threads * sizeof(uint4); }
+
+template <int R>
+__device__ static __forceinline__ void ssw_snap_init(SswSnap<R>& sn, uint4* area, int tid)
 {
-#ifndef SSW_CPU_EMU
-	asm volatile("" : : "l"(&sn) : "memory");       /* the snapshot must live in memory, not in 2R more registers */
-#endif
+	sn.base = area + (size_t)tid * (2 * SswSnap<R>::Q + 1);
 #pragma unroll
-	for (int k = 0; k < R; ++k) { sn.w[0][k] = 0; sn.w[1][k] = 0; }
+	for (int i = 0; i < 2 * SswSnap<R>::Q; ++i) sn.base[i] = make_uint4(0, 0, 0, 0);
 }
 
 template <int R>
-__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, SswSnap<R>& sn, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1)
+__device__ static __forceinline__ void ssw_snap_store(const SswSnap<R>& sn, int h, const uint32_t (&Hn)[R])
+{
+	constexpr int Q = SswSnap<R>::Q;
+#pragma unroll
+	for (int q = 0; q < Q; ++q)
+		sn.base[h * Q + q] = make_uint4(Hn[4 * q], 4 * q + 1 < R ? Hn[4 * q + 1] : 0u, 4 * q + 2 < R ? Hn[4 * q + 2] : 0u, 4 * q + 3 < R ? Hn[4 * q + 3] : 0u);
+}
+
+template <int R>
+__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, const SswSnap<R>& sn, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1)
 {
 #ifndef SSW_CPU_EMU
-	asm volatile("" : "+r"(sp));                /* keep the range test inside this rare path */
+	asm volatile("" : "+r"(sp));                /* keep the range test inside this path */
 #endif
 	if (sp >= p0 && sp < p1) {
-		if (half_of(nb, 0) > half_of(lb.best, 0)) {
-			lb.pos0 = sp;
-#pragma unroll
-			for (int k = 0; k < R; ++k) sn.w[0][k] = Hn[k];
-		}
-		if (half_of(nb, 1) > half_of(lb.best, 1)) {
-			lb.pos1 = sp;
-#pragma unroll
-			for (int k = 0; k < R; ++k) sn.w[1][k] = Hn[k];
-		}
+		if (half_of(nb, 0) > half_of(lb.best, 0)) { lb.pos0 = sp; ssw_snap_store<R>(sn, 0, Hn); }
+		if (half_of(nb, 1) > half_of(lb.best, 1)) { lb.pos1 = sp; ssw_snap_store<R>(sn, 1, Hn); }
 		lb.best = nb;
 	}
 }
@@ -239,11 +248,18 @@ __device__ static __forceinline__ void ssw_track(SswLaneBest& lb, SswSnap<R>& sn
 template <int R>
 __device__ static __forceinline__ void ssw_track_rows(SswLaneBest& lb, const SswSnap<R>& sn, int row_base)
 {
+	constexpr int Q = SswSnap<R>::Q;
 	lb.row0 = SSW_NO_ROW; lb.row1 = SSW_NO_ROW;
 #pragma unroll
-	for (int k = R - 1; k >= 0; --k) {
-		if (half_of(sn.w[0][k], 0) == half_of(lb.best, 0)) lb.row0 = row_base + k;
-		if (half_of(sn.w[1][k], 1) == half_of(lb.best, 1)) lb.row1 = row_base + k;
+	for (int q = Q - 1; q >= 0; --q) {
+		const uint4 a = sn.base[q], b = sn.base[Q + q];
+		const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+		for (int j = 3; j >= 0; --j) {
+			if (4 * q + j >= R) continue;
+			if (half_of(wa[j], 0) == half_of(lb.best, 0)) lb.row0 = row_base + 4 * q + j;
+			if (half_of(wb[j], 1) == half_of(lb.best, 1)) lb.row1 = row_base + 4 * q + j;
+		}
 	}
 }
 
@@ -356,7 +372,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	SswLaneBest lb;
 	lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
 	SswSnap<R> snap;
-	ssw_snap_pin<R>(snap);
+	ssw_snap_init<R>(snap, reinterpret_cast<uint4*>(smem + (size_t)(share ? 1 : nwarps) * (size_t)(n + 1) * 32 * R), (int)threadIdx.x);
 	uint32_t blk_acc = 0;                               /* CM == 2: running maximum of the current block (last lane) */
 
 	for (int body = 0; body < n_body; ++body) {
@@ -541,11 +557,12 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 	const int s_first = part * per_part, s_last = min(T.n_strips, s_first + per_part);      /* this CTA's strips [s_first, s_last) */
 	volatile int* gprog_in = gsync + 1 + (SPLIT ? unit - 1 : 0);          /* published by the previous block of the same task */
 	volatile int* gprog_out = gsync + 1 + (SPLIT ? unit : 0);
-	/* shared memory: NW profiles, then prog[n_strips], then the stop flag */
+	/* shared memory: NW profiles, then prog[n_strips], the stop flag and the done bits, then (16-byte aligned) the snapshot area */
 	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
 	volatile int* prog = reinterpret_cast<volatile int*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R);
 	volatile int* stop = prog + T.n_strips;                /* 1: every requested half has met its score (reverse pass) */
 	volatile int* done = stop + 1;                          /* bit h: half h has met its score */
+	uint4* snap_area = reinterpret_cast<uint4*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R + (size_t)((T.n_strips + 2 + 3) / 4 * 4));
 	const int need_mask = (T.term_a >= 0 ? 1 : 0) | (T.term_b >= 0 ? 2 : 0);
 	for (int i = threadIdx.x; i < T.n_strips; i += blockDim.x) prog[i] = -0x40000000;
 	if (threadIdx.x == 0) { *stop = 0; *done = 0; }
@@ -587,7 +604,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 			SswLaneBest lb;
 			lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
 			SswSnap<R> snap;
-			ssw_snap_pin<R>(snap);
+			ssw_snap_init<R>(snap, snap_area, (int)threadIdx.x);
 
 			const uint32_t* bin = bnd + T.bnd_off + (size_t)((s + 1) & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;   /* written by strip s-1 */
 			uint32_t* bout = bnd + T.bnd_off + (size_t)(s & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;

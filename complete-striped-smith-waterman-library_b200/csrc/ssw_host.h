@@ -9,6 +9,7 @@
 #include <mutex>
 #include <thread>
 #include <utility>
+#include <vector>
 #include "ssw_common.cuh"
 
 /* counts device allocations and frees made through SswDevBuf: the engine re-reads the free device memory only when
@@ -158,6 +159,27 @@ struct SswStagedD2H {
 struct ssw_engine;
 extern "C" int ssw_engine_set_pair(ssw_engine* e, const int8_t* read, int32_t readLen, const int8_t* ref, int32_t refLen);
 int ssw_default_engines_option(const char* name, int64_t value);     /* ssw_engine_set_option(NULL, ...): the engines behind ssw_align */
+
+/* Phase times without synchronising: start/stop only record events on the stream; the elapsed times are read and added
+ * to their accumulators by collect(), once, after the call's final synchronisation.  (A stopwatch that waits for its stop
+ * event costs one host<->device round trip per kernel: three per phase of a one-pair ssw_align.) */
+struct SswLaps {
+	struct Lap { cudaEvent_t a, b; float* acc; };
+	std::vector<cudaEvent_t> pool;
+	std::vector<Lap> laps;
+	size_t used = 0;
+	cudaEvent_t cur = nullptr;
+	cudaEvent_t get() { if (used == pool.size()) { cudaEvent_t ev = nullptr; cudaEventCreate(&ev); pool.push_back(ev); } return pool[used++]; }
+	void start(cudaStream_t s) { cur = get(); cudaEventRecord(cur, s); }
+	void stop(cudaStream_t s, float* acc) { cudaEvent_t b = get(); cudaEventRecord(b, s); laps.push_back(Lap{cur, b, acc}); }
+	/* all recorded events must have completed (the caller has synchronised the stream) */
+	void collect()
+	{
+		for (const Lap& l : laps) { float ms = 0; if (cudaEventElapsedTime(&ms, l.a, l.b) == cudaSuccess) *l.acc += ms; }
+		laps.clear(); used = 0;
+	}
+	~SswLaps() { for (cudaEvent_t ev : pool) if (ev) cudaEventDestroy(ev); }
+};
 
 /* CUDA-event stopwatch on one stream */
 struct SswTimer {
