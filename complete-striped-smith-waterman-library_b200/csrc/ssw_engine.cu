@@ -130,6 +130,27 @@ struct ssw_engine {
 
 struct FillPtrs { const SswItem* items; uint32_t* cm; SswItemBest* bests; };
 
+/* Warps per CTA of a forward launch with a CTA-shared profile: 8 instead of 4 when that doubles the resident warps per SM
+ * (large alphabets: the profile, not the registers, limits the CTAs per SM). */
+template <int R>
+static int fill_warps_shared(int n)
+{
+	if (R < 16) return SSW_FILL_WARPS;
+	const size_t prof = ssw_fill_smem_bytes<R>(n, 1), snap = ssw_snap_smem_bytes<R>(32), sm = (size_t)227 * 1024;
+	const size_t s4 = prof + snap * 4 + 1024, s8 = prof + snap * 8 + 1024;
+	const int occ4 = (int)std::min<size_t>(SSW_FILL_MINB, sm / s4), occ8 = (int)std::min<size_t>(2, sm / s8);
+	return occ8 * 8 > occ4 * 4 ? 8 : SSW_FILL_WARPS;
+}
+static int fill_warps_of(int inst, int n, int share)
+{
+	if (!share) return SSW_FILL_WARPS;
+	switch (kInst[inst].R) {
+	case 16: return fill_warps_shared<16>(n);
+	case 20: return fill_warps_shared<20>(n);
+	default: return SSW_FILL_WARPS;
+	}
+}
+
 template <int G, int R>
 static int launch_fill(ssw_engine* e, const FillPtrs& fp, int n_items, int dir, int cm_mode, int share, const ssw_batch_params& P)
 {
@@ -138,6 +159,7 @@ static int launch_fill(ssw_engine* e, const FillPtrs& fp, int n_items, int dir, 
 	const size_t warp_smem = ssw_fill_smem_bytes<R>(P.n, 1), warp_snap = ssw_snap_smem_bytes<R>(32);
 	int warps = SSW_FILL_WARPS;
 	if (!share) while (warps > 1 && (warp_smem + warp_snap) * warps > 200 * 1024) --warps;
+	else if (dir > 0) warps = fill_warps_shared<R>(P.n);
 	const int per_cta = warps * GPW;
 	const int grid = (n_items + per_cta - 1) / per_cta;
 	const size_t smem = (share ? warp_smem : warp_smem * warps) + warp_snap * warps;       /* profile(s), then the best-cell snapshots */
@@ -148,16 +170,22 @@ static int launch_fill(ssw_engine* e, const FillPtrs& fp, int n_items, int dir, 
 	const int8_t* mat = e->d_mat.as<int8_t>();
 	uint32_t* cm = fp.cm;
 	SswItemBest* bests = fp.bests;
-#define SSW_FILL_GO(DIR, CM, TERM)                                                                               \
+#define SSW_FILL_GO(DIR, CM, TERM, W)                                                                            \
 	do {                                                                                                         \
-		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM>;                                                        \
+		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM, W>;                                                     \
 		if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem)) return -1;                           \
 		ssw_launch(kern, dim3(grid), dim3(warps * 32), smem, e->stream, items, n_items, q, r, mat, (int)P.n,     \
 		           (int)P.gap_open, (int)P.gap_extend, cm, bests, share);                                        \
 	} while (0)
-	if (dir > 0) { if (cm_mode == 2) SSW_FILL_GO(1, 2, false); else SSW_FILL_GO(1, 1, false); }   /* forward: column maxima per column or per block */
-	else {
-		if constexpr (G == 32) SSW_FILL_GO(-1, 0, true);   /* reverse: one alignment per warp, early termination */
+	if (dir > 0) {   /* forward: column maxima per column or per block */
+		if (warps == 8) {
+			if constexpr (R >= 16) { if (cm_mode == 2) SSW_FILL_GO(1, 2, false, 8); else SSW_FILL_GO(1, 1, false, 8); }
+			else return -2;
+		}
+		else if (cm_mode == 2) SSW_FILL_GO(1, 2, false, SSW_FILL_WARPS);
+		else SSW_FILL_GO(1, 1, false, SSW_FILL_WARPS);
+	} else {
+		if constexpr (G == 32) SSW_FILL_GO(-1, 0, true, SSW_FILL_WARPS);   /* reverse: one alignment per warp, early termination */
 		else return -2;
 	}
 #undef SSW_FILL_GO
@@ -211,7 +239,16 @@ template <int G, int R>
 static int fill_occ_of(int n)
 {
 	int occ = 0;
-	const size_t smem = ssw_fill_smem_bytes<R>(n, 1) + ssw_snap_smem_bytes<R>(SSW_FILL_THREADS);
+	const int warps = fill_warps_shared<R>(n);
+	const size_t smem = ssw_fill_smem_bytes<R>(n, 1) + ssw_snap_smem_bytes<R>(warps * 32);
+	if (warps == 8) {
+		if constexpr (R >= 16) {
+			auto kern = ssw_fill_kernel<G, R, 1, 2, false, 8>;
+			ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess) occ = 1;
+		}
+		return occ > 0 ? occ : 1;
+	}
 	auto kern = ssw_fill_kernel<G, R, 1, 2, false>;
 	ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SSW_FILL_THREADS, smem) != cudaSuccess) occ = 1;
@@ -873,7 +910,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	while (k < pts.size()) {
 		/* one launch = one kernel instance, bounded by the column-maximum budget */
 		const int inst = pts[k].inst;
-		const int per_cta = SSW_FILL_WARPS * (32 / kInst[inst].G);   /* share == 1 launches always use SSW_FILL_WARPS warps */
+		const int per_cta = fill_warps_of(inst, P.n, 1) * (32 / kInst[inst].G);   /* items per CTA of a launch with CTA-shared profiles */
 		size_t k_end = k, cm_words = 0;
 		int64_t total_cols = 0;
 		/* Column maxima: one word per column, or -- long references in a launch that fills the device -- one word per block of
@@ -1223,7 +1260,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 	size_t k = 0;
 	while (k < order.size()) {
 		const int inst = q_inst[order[k]];
-		const int per_cta = SSW_FILL_WARPS * (32 / kInst[inst].G);
+		const int per_cta = fill_warps_of(inst, P.n, 1) * (32 / kInst[inst].G);
 		const int n_r_pad = (n_r + per_cta - 1) / per_cta * per_cta;
 		/* query pairs of this launch: same instance, bounded by memory */
 		const size_t per_qp = (size_t)cm_per_qp * 4 + (size_t)n_r_pad * (sizeof(SswItem) + sizeof(SswItemBest)) + (size_t)n_r * 2 * (sizeof(SswAlnDesc) + sizeof(SswFillResult));

@@ -301,8 +301,10 @@ __device__ static __forceinline__ void ssw_reduce_best(const SswLaneBest& lb, in
  *   2  one packed word per block of SSW_CM_BLOCK columns.  The second-best scan (ssw.c:368-381) needs single columns
  *      only in the <= 2 blocks cut by the mask window and in the block that holds the winner; ssw_resolve.cuh
  *      re-fills those three blocks per alignment with mode 1.  Chunks start at multiples of SSW_CM_BLOCK. */
-template <int G, int R, int DIR, int CM, bool TERM>
-__global__ void __launch_bounds__(SSW_FILL_THREADS, SSW_FILL_MINB)
+/* WARPS: warps per CTA.  4 by default; 8 where one CTA-shared profile is so large (protein alphabets: 64 KB at 20 rows per
+ * lane) that four-warp CTAs would leave the SM with 8 resident warps -- eight warps per profile keep 16. */
+template <int G, int R, int DIR, int CM, bool TERM, int WARPS = SSW_FILL_WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == SSW_FILL_WARPS ? SSW_FILL_MINB : 2)
 ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
                 const int8_t* __restrict__ mat, int n, int gapO, int gapE,

@@ -20,7 +20,7 @@ with open(fa, "w") as f:
     f.write(">chr1\n" + "\n".join(s[i:i + 70] for i in range(0, len(s), 70)) + "\n")
 with open(fq, "w") as f:
     for i, r in enumerate(g["reads"]):
-        f.write(">read%d\n%s\n" % (i, "".join(L[c] for c in r)))
+        f.write(">read%d\n%s\n" % (i, r if isinstance(r, str) else "".join(L[c] for c in r)))
 exes = {"ssw_test_ref": os.path.join(ROOT, "oracle", "_ref", "ssw_test_ref"), "ssw_test_b200": os.path.join(ROOT, "oracle", "_ref", "ssw_test_b200"),
         "ssw_batch_cli": os.path.join(ROOT, "complete-striped-smith-waterman-library_b200", "ssw_batch_cli")}
 out = {}
