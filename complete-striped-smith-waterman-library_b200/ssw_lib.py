@@ -198,7 +198,7 @@ class BatchAligner(object):
             n_pairs = len(pq_a)
             pq = pq_a.ctypes.data_as(ct.POINTER(ct.c_int32))
             pr = pr_a.ctypes.data_as(ct.POINTER(ct.c_int32))
-        res = np.zeros(n_pairs, dtype=RESULT_DTYPE)
+        res = np.empty(n_pairs, dtype=RESULT_DTYPE)         # every record is written by the library
         if want_cigar is None:
             want_cigar = bool(flag & 7)
         cap = 0
@@ -207,7 +207,7 @@ class BatchAligner(object):
             QL = np.repeat(ql, len(rl)) if pair_query is None else ql[pq_a]
             RL = np.tile(rl, len(ql)) if pair_query is None else rl[pr_a]
             cap = int(np.sum(QL + np.minimum(RL, QL * 128) + 4))
-        pool = np.zeros(max(cap, 1), dtype=np.uint32)
+        pool = np.empty(max(cap, 1), dtype=np.uint32)        # worst-case sized, only pool[:used] is meaningful
         used = ct.c_int64(0)
         rv = self.lib.ssw_engine_align(self.h, ct.byref(P), n_pairs, pq, pr, res.ctypes.data_as(ct.c_void_p),
                                        pool.ctypes.data_as(ct.POINTER(ct.c_uint32)), len(pool), ct.byref(used))

@@ -2,7 +2,8 @@
 """Time one BASELINE.json configuration on one GPU through the batch ABI and print the engine's breakdown.
   python tools/run_config.py 5 [--reads N] [--flag F]     config 5: 10 kbp reads x 100 kbp reference (word path, CIGAR)
   python tools/run_config.py 4 [--queries Q --targets T]  config 4: protein BLOSUM50 300 aa x 400 aa (word path)
-  python tools/run_config.py 2                            config 2 (same as bench.py's workload)
+  python tools/run_config.py 2                            config 2 (1,000 x 150 bp vs 5 Mbp)
+  python tools/run_config.py 3 --reads 100000             config 3 (bench.py's headline batch on one GPU)
 """
 import argparse, json, os, sys, time
 import numpy as np
@@ -41,6 +42,10 @@ elif a.config == 4:
             seg = q[50:250].copy(); m = rt.random(200) < 0.2; seg[m] = rt.integers(0, 20, size=int(m.sum())); s[100:300] = seg
         rs.append(s)
     mat, n, flag, ml, ss = C.BLOSUM50, 24, (0 if a.flag < 0 else a.flag), 150, 1
+elif a.config == 3:
+    ref, reads = C.make_dna_workload(5_000_000, a.reads, 150, seed_ref=1001, seed_reads=3003)
+    mat, n, flag, ml, ss = C.dna_matrix(2, 2), 5, (0 if a.flag < 0 else a.flag), 75, 2
+    qs, rs = reads, [ref]
 else:
     ref, reads = C.make_dna_workload(5_000_000, a.reads, 150, seed_ref=1001, seed_reads=2002)
     mat, n, flag, ml, ss = C.dna_matrix(2, 2), 5, (0 if a.flag < 0 else a.flag), 75, 2
