@@ -250,104 +250,74 @@ __device__ static __forceinline__ void ssw_tb_row_group(int i, int j0, int beg, 
 	}
 }
 
-/*
- * Fast variant for bands up to SSW_TBP_MAXBW: one warp per alignment, four alignments per CTA.  The two live H/E
- * rows sit in shared memory (indexed by reference column modulo the ring width), the scoring matrix too, so a
- * tile's critical path has no global-memory latency.  After the fill the warp stages blocks of direction bytes into
- * its (now free) row memory with coalesced loads and lane 0 walks the traceback inside them: the plain walk pays a
- * DRAM latency per step because every step moves up one band row.
- */
-#define SSW_TBP_MAXBW 990
+/* Row ring width (ints, a power of two) for a band of half-width bw: the live part of a row spans 2*bw + 1 columns, the
+ * tiles of a row group may run up to 64 columns beyond it. */
+__host__ __device__ static __forceinline__ int ssw_tb_ring_of(int bw)
+{
+	int r = 128;
+	while (r < 2 * bw + 66) r <<= 1;
+	return r;
+}
 
-__global__ void __launch_bounds__(SSW_TB_THREADS)
-ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
-                       const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
-                       const int8_t* __restrict__ mat, int n, int gapO, int gapE,
-                       uint8_t* __restrict__ dir_base, uint32_t* __restrict__ cig_base, int ring)
+/* One banded fill (ssw.c:628-676) by one warp: rows in the warp's shared-memory ring `mine` (4 x ring ints), direction bytes
+ * to `dir`, returns the first row-major cell holding the maximum of this band (all lanes). */
+__device__ static __forceinline__ void ssw_tb_band_fill(int lane, int ql, int rl, int bw, const int8_t* ref, const int8_t* read,
+                                                       const int8_t* smat, int n, int gapO, int gapE, int g,
+                                                       int32_t* mine, int ring, uint8_t* dir, int& bestv, int& besti, int& bestj)
 {
 	constexpr unsigned FULL = 0xffffffffu;
-	SSW_DYN_SMEM(int32_t, smem);                                  /* [warp][4][ring] ints, then n*n matrix bytes */
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int8_t* smat = reinterpret_cast<int8_t*>(smem + (size_t)SSW_TB_WARPS * 4 * ring);
-	for (int k = threadIdx.x; k < n * n; k += blockDim.x) smat[k] = mat[k];
-	__syncthreads();
-	const int ti = (int)blockIdx.x * SSW_TB_WARPS + warp;
-	if (ti >= n_tasks) return;
-	SswTbTask T = tasks[ti];
-	const int8_t* ref = refs + T.ref_off;
-	const int8_t* read = qcodes + T.read_off;
-	const int rl = T.ref_len, ql = T.read_len;
 	const int mask = ring - 1;
-	const int g = gapO < gapE ? gapO : gapE;
-	uint8_t* dir = dir_base + T.dir_off + 1;
-	int32_t* mine = smem + (size_t)warp * 4 * ring;
+	const int W = 2 * bw + 1;
 	int32_t* Hrow[2] = {mine, mine + ring};
 	int32_t* Erow[2] = {mine + 2 * ring, mine + 3 * ring};
-	const int len = rl > ql ? rl : ql;
-	const long long c0 = clock64();
-	int bw = T.bw, W = 2 * bw + 1;
-
-	/* band-doubling loop of banded_sw (ssw.c:616-680), kept inside the kernel while the doubled band still fits the
-	 * row ring: only the last band's directions are needed, and the running maximum is carried in T */
-	for (;;) {
-		W = 2 * bw + 1;
-		int bestv = 0, besti = 0, bestj = 0;
-		int rd_next = (int)read[0];
-		for (int i = 0; i < ql; ++i) {
-			const int cur = i & 1, prv = cur ^ 1;
-			const int beg = max(0, i - bw), end = min(rl - 1, i + bw);
-			const int pbeg = max(0, i - 1 - bw);
-			const bool top_oob = (i <= bw + 1) || (end == i + bw);
-			const int rd = rd_next;
-			if (i + 1 < ql) rd_next = (int)read[i + 1];
-			uint8_t* drow = dir + (size_t)W * i - beg;
-			{
-				int carryF = -gapO, carryH = 0, carryFp = 0;
-				int j0 = beg;
-				while (j0 <= end) {
-					const int tiles = (end - j0) / 32 + 1;
-					if (tiles >= 3) {
-						ssw_tb_row_group<4>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
-						                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
-						j0 += 128;
-					} else if (tiles == 2) {
-						ssw_tb_row_group<2>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
-						                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
-						j0 += 64;
-					} else {
-						ssw_tb_row_group<1>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
-						                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
-						j0 += 32;
-					}
+	bestv = 0; besti = 0; bestj = 0;
+	int rd_next = (int)read[0];
+	for (int i = 0; i < ql; ++i) {
+		const int cur = i & 1, prv = cur ^ 1;
+		const int beg = max(0, i - bw), end = min(rl - 1, i + bw);
+		const int pbeg = max(0, i - 1 - bw);
+		const bool top_oob = (i <= bw + 1) || (end == i + bw);
+		const int rd = rd_next;
+		if (i + 1 < ql) rd_next = (int)read[i + 1];
+		uint8_t* drow = dir + (size_t)W * i - beg;
+		{
+			int carryF = -gapO, carryH = 0, carryFp = 0;
+			int j0 = beg;
+			while (j0 <= end) {
+				const int tiles = (end - j0) / 32 + 1;
+				if (tiles >= 3) {
+					ssw_tb_row_group<4>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
+					                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
+					j0 += 128;
+				} else if (tiles == 2) {
+					ssw_tb_row_group<2>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
+					                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
+					j0 += 64;
+				} else {
+					ssw_tb_row_group<1>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
+					                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
+					j0 += 32;
 				}
 			}
-			__syncwarp();
 		}
-#pragma unroll
-		for (int off = 16; off >= 1; off >>= 1) {
-			const int ov = __shfl_xor_sync(FULL, bestv, off), oi = __shfl_xor_sync(FULL, besti, off), oj = __shfl_xor_sync(FULL, bestj, off);
-			if (ov > bestv || (ov == bestv && (oi < besti || (oi == besti && oj < bestj)))) { bestv = ov; besti = oi; bestj = oj; }
-		}
-		if (bestv > T.max) { T.max = bestv; T.max_i = besti; T.max_j = bestj; }     /* strict, carried across doublings */
-		if (!(T.max < T.score && 2 * bw <= len)) break;                              /* ssw.c:678-679: done */
-		if (2 * (2 * bw) + 66 > ring) {                                              /* the next band needs a wider ring: back to the host */
-			T.bw = bw;
-			if (lane == 0) { T.status = SSW_TB_WIDER; tasks[ti] = T; }
-			return;
-		}
-		bw *= 2;
 		__syncwarp();
 	}
-	T.bw = bw;
-	const long long c1 = clock64();
-	T.dbg_fill = c1 - c0; T.dbg_walk = 0; T.dbg_score = 0;
-	__threadfence_block();
-	__syncwarp();
+#pragma unroll
+	for (int off = 16; off >= 1; off >>= 1) {
+		const int ov = __shfl_xor_sync(FULL, bestv, off), oi = __shfl_xor_sync(FULL, besti, off), oj = __shfl_xor_sync(FULL, bestj, off);
+		if (ov > bestv || (ov == bestv && (oi < besti || (oi == besti && oj < bestj)))) { bestv = ov; besti = oi; bestj = oj; }
+	}
+}
 
-	/* ---- traceback (ssw.c:683-762), staged through the warp's row memory ---- */
-	uint32_t* cig = cig_base + T.cig_off;
-	uint8_t* stage = reinterpret_cast<uint8_t*>(mine);
-	const int stage_bytes = 4 * ring * (int)sizeof(int32_t);
+/* Traceback (ssw.c:683-762) of the finished band T.bw by one warp, staged through `stage` (shared memory, stage_bytes): the warp
+ * copies blocks of direction bytes with coalesced loads and lane 0 walks inside them (the plain walk pays a DRAM latency per
+ * step because every step moves up one band row); then the CIGAR re-scoring (ssw.c:785-811).  Writes the task record. */
+__device__ static __forceinline__ void ssw_tb_walk(SswTbTask& T, SswTbTask* slot, int lane, const uint8_t* dir, uint8_t* stage, int stage_bytes,
+                                                  uint32_t* cig, const int8_t* smat, const int8_t* ref, const int8_t* read, int n,
+                                                  int gapO, int gapE, long long c1)
+{
+	constexpr unsigned FULL = 0xffffffffu;
+	const int bw = T.bw, W = 2 * bw + 1, ql = T.read_len;
 	const long long dir_cells = (long long)W * ql;
 	const int rows_per_block = max(1, (stage_bytes - 8) / W);
 	int wi = T.max_i, wj = T.max_j, e = 0, l = 0, state = 2, op = 0, prev = 0;
@@ -386,7 +356,7 @@ ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
 	if (lane != 0) return;
 	const long long c2 = clock64();
 	T.dbg_walk = c2 - c1;
-	if (bad) { T.status = SSW_TB_ERROR; T.cig_len = 0; tasks[ti] = T; return; }
+	if (bad) { T.status = SSW_TB_ERROR; T.cig_len = 0; *slot = T; return; }
 	if (op == 0) cig[l++] = ssw_tb_pack((uint32_t)(e + 1), 0);
 	else { cig[l++] = ssw_tb_pack((uint32_t)e, (uint32_t)op); cig[l++] = ssw_tb_pack(1, 0); }
 	for (int a = 0, b2 = l - 1; a < b2; ++a, --b2) { const uint32_t tmp = cig[a]; cig[a] = cig[b2]; cig[b2] = tmp; }
@@ -404,7 +374,146 @@ ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
 	T.cig_len = l;
 	T.status = sc == T.score ? SSW_TB_OK : SSW_TB_MISMATCH;
 	T.dbg_score = clock64() - c2;
-	tasks[ti] = T;
+	*slot = T;
+}
+
+/*
+ * Fast variant for bands up to SSW_TBP_MAXBW: one warp per alignment, four alignments per CTA.  The two live H/E
+ * rows sit in shared memory (indexed by reference column modulo the ring width), the scoring matrix too, so a
+ * tile's critical path has no global-memory latency.  After the fill the warp stages blocks of direction bytes into
+ * its (now free) row memory with coalesced loads and lane 0 walks the traceback inside them.
+ */
+#define SSW_TBP_MAXBW 990
+
+__global__ void __launch_bounds__(SSW_TB_THREADS)
+ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
+                       const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
+                       const int8_t* __restrict__ mat, int n, int gapO, int gapE,
+                       uint8_t* __restrict__ dir_base, uint32_t* __restrict__ cig_base, int ring)
+{
+	SSW_DYN_SMEM(int32_t, smem);                                  /* [warp][4][ring] ints, then n*n matrix bytes */
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int8_t* smat = reinterpret_cast<int8_t*>(smem + (size_t)SSW_TB_WARPS * 4 * ring);
+	for (int k = threadIdx.x; k < n * n; k += blockDim.x) smat[k] = mat[k];
+	__syncthreads();
+	const int ti = (int)blockIdx.x * SSW_TB_WARPS + warp;
+	if (ti >= n_tasks) return;
+	SswTbTask T = tasks[ti];
+	const int8_t* ref = refs + T.ref_off;
+	const int8_t* read = qcodes + T.read_off;
+	const int rl = T.ref_len, ql = T.read_len;
+	const int g = gapO < gapE ? gapO : gapE;
+	uint8_t* dir = dir_base + T.dir_off + 1;
+	int32_t* mine = smem + (size_t)warp * 4 * ring;
+	const int len = rl > ql ? rl : ql;
+	const long long c0 = clock64();
+	int bw = T.bw;
+
+	/* band-doubling loop of banded_sw (ssw.c:616-680), kept inside the kernel while the doubled band still fits the
+	 * row ring: only the last band's directions are needed, and the running maximum is carried in T */
+	for (;;) {
+		int bestv, besti, bestj;
+		ssw_tb_band_fill(lane, ql, rl, bw, ref, read, smat, n, gapO, gapE, g, mine, ring, dir, bestv, besti, bestj);
+		if (bestv > T.max) { T.max = bestv; T.max_i = besti; T.max_j = bestj; }     /* strict, carried across doublings */
+		if (!(T.max < T.score && 2 * bw <= len)) break;                              /* ssw.c:678-679: done */
+		if (2 * (2 * bw) + 66 > ring) {                                              /* the next band needs a wider ring: back to the host */
+			T.bw = bw;
+			if (lane == 0) { T.status = SSW_TB_WIDER; tasks[ti] = T; }
+			return;
+		}
+		bw *= 2;
+		__syncwarp();
+	}
+	T.bw = bw;
+	const long long c1 = clock64();
+	T.dbg_fill = c1 - c0; T.dbg_walk = 0; T.dbg_score = 0;
+	__threadfence_block();
+	__syncwarp();
+	ssw_tb_walk(T, tasks + ti, lane, dir, reinterpret_cast<uint8_t*>(mine), 4 * ring * (int)sizeof(int32_t), cig_base + T.cig_off,
+	            smat, ref, read, n, gapO, gapE, c1);
+}
+
+/*
+ * Speculative variant: one CTA per alignment, warp w fills band T.bw << w -- the band-doubling rounds of banded_sw
+ * (ssw.c:616-680) side by side instead of one after the other.  A round is a chain of dependent rows (about one tile's
+ * scan latency per row whatever the band, up to four tiles), so the rounds of a task cost the time of the widest one instead
+ * of their sum; the device is nearly idle during this phase, the extra bands are free.  The reference's sequence is
+ * reproduced from the per-round results: the running maximum and its cell persist across rounds with strict '>'
+ * (ssw.c:601,667-671), i.e. round k contributes its first row-major maximum only if that exceeds every earlier round's;
+ * the first round after which `max >= score || 2*bw > len` is the band the traceback walks (later rounds are discarded).
+ * If no speculated round ends the loop the task goes back to the host with the last band tried (status WIDER).
+ * Shared memory: the scoring matrix, then the row rings of the rounds (4 x ssw_tb_ring_of(bw_w) ints each).  Direction
+ * bytes: round w at dir_off + sum of the earlier rounds' (16-byte aligned) sizes.
+ */
+#define SSW_TBS_MAXW 8
+__host__ __device__ static __forceinline__ size_t ssw_tb_dir_bytes(int bw, int read_len) { return (((size_t)(2 * bw + 1) * (size_t)read_len + 2) + 15) / 16 * 16; }
+
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(SSW_TBS_MAXW * 32)
+ssw_banded_spec_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
+                       const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
+                       const int8_t* __restrict__ mat, int n, int gapO, int gapE,
+                       uint8_t* __restrict__ dir_base, uint32_t* __restrict__ cig_base, int nw)
+{
+	SSW_DYN_SMEM(int32_t, smem);
+	__shared__ int s_best[SSW_TBS_MAXW][3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int mat_ints = (n * n + 15) / 16 * 4;
+	int8_t* smat = reinterpret_cast<int8_t*>(smem);
+	for (int k = threadIdx.x; k < n * n; k += blockDim.x) smat[k] = mat[k];
+	__syncthreads();
+	const int ti = (int)blockIdx.x;
+	if (ti >= n_tasks) return;
+	SswTbTask T = tasks[ti];
+	const int8_t* ref = refs + T.ref_off;
+	const int8_t* read = qcodes + T.read_off;
+	const int rl = T.ref_len, ql = T.read_len;
+	const int g = gapO < gapE ? gapO : gapE;
+	const int len = rl > ql ? rl : ql;
+	const long long c0 = clock64();
+	/* geometry of this warp's round; rounds behind one whose band already exceeds `len` can never run (ssw.c:679) */
+	int bw = T.bw, ring_off = mat_ints;
+	size_t dir_off = 0;
+	bool possible = true;
+	for (int w = 0; w < warp; ++w) {
+		if (!(2 * bw <= len)) possible = false;
+		ring_off += 4 * ssw_tb_ring_of(bw);
+		dir_off += ssw_tb_dir_bytes(bw, ql);
+		bw *= 2;
+	}
+	int total_ints = ring_off;
+	{
+		int b2 = bw;
+		for (int w = warp; w < nw; ++w) { total_ints += 4 * ssw_tb_ring_of(b2); b2 *= 2; }
+	}
+	uint8_t* dir = dir_base + T.dir_off + dir_off + 1;
+	if (warp < nw && possible) {
+		int bestv, besti, bestj;
+		ssw_tb_band_fill(lane, ql, rl, bw, ref, read, smat, n, gapO, gapE, g, smem + ring_off, ssw_tb_ring_of(bw), dir, bestv, besti, bestj);
+		if (lane == 0) { s_best[warp][0] = bestv; s_best[warp][1] = besti; s_best[warp][2] = bestj; }
+	}
+	__threadfence_block();
+	__syncthreads();
+	if (warp != 0) return;
+	/* the reference's sequence over the rounds */
+	int kb = T.bw, done = -1, last_bw = T.bw;
+	size_t koff = 0, done_off = 0;
+	for (int w = 0; w < nw; ++w) {
+		if (s_best[w][0] > T.max) { T.max = s_best[w][0]; T.max_i = s_best[w][1]; T.max_j = s_best[w][2]; }
+		last_bw = kb;
+		if (!(T.max < T.score && 2 * kb <= len)) { done = w; done_off = koff; break; }
+		koff += ssw_tb_dir_bytes(kb, ql);
+		kb *= 2;
+	}
+	T.bw = last_bw;
+	const long long c1 = clock64();
+	T.dbg_fill = c1 - c0; T.dbg_walk = 0; T.dbg_score = 0;
+	if (done < 0) {
+		if (lane == 0) { T.status = SSW_TB_WIDER; tasks[ti] = T; }
+		return;
+	}
+	ssw_tb_walk(T, tasks + ti, lane, dir_base + T.dir_off + done_off + 1, reinterpret_cast<uint8_t*>(smem + mat_ints),
+	            (total_ints - mat_ints) * (int)sizeof(int32_t), cig_base + T.cig_off, smat, ref, read, n, gapO, gapE, c1);
 }
 
 /* General variant (any band width): one warp per alignment, H/E rows in global memory. */
@@ -498,6 +607,7 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
                              const int8_t* d_q, const int8_t* d_r, const int8_t* d_mat, int n, int gapO, int gapE,
                              SswDevBuf* scratch, float* ms_acc, int64_t* launches,
                              int tb_maxbw /* "tb_maxbw" option: bands above this use the global-memory kernel (tests: 0) */,
+                             int tb_spec /* "tb_spec" option: 0 = band-doubling rounds one after the other (no speculative kernel) */,
                              const std::function<int(size_t, const uint32_t*, int32_t, int)>& emit)
 {
 	std::vector<size_t> active(tasks.size());
@@ -510,8 +620,27 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 	}
 	const size_t free_b = ssw_free_device_bytes();
 	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + scratch->cap) / 2);
-	auto ring_of = [tb_maxbw](const SswTbTask& t) -> int {          /* 0: single-warp kernel with global row buffers */
+	/* Rounds of band doubling run side by side by the speculative kernel (1: not used).  Narrow bands (up to four tiles per row)
+	 * cost one tile latency per row whatever their width, so all of them go together; of wider ones at most two, so that
+	 * a task that needs only the first loses little. */
+	auto spec_rounds = [tb_maxbw, tb_spec](const SswTbTask& t) -> int {
+		if (!tb_spec) return 1;
+		const int len = std::max(t.ref_len, t.read_len);
+		int nw = 0, bw = t.bw;
+		while (nw < SSW_TBS_MAXW && bw <= tb_maxbw) {
+			if (nw >= 2 && 2 * bw + 1 > 129) break;
+			++nw;
+			if (!(2 * bw <= len)) break;
+			bw *= 2;
+		}
+		return nw;
+	};
+	/* kernel shape of a task: > 0 row-ring width of the one-warp shared-memory kernel, 0 the global-memory kernel,
+	 * < 0 minus the number of rounds of the speculative kernel */
+	auto ring_of = [tb_maxbw, &spec_rounds](const SswTbTask& t) -> int {
 		if (t.bw > tb_maxbw) return 0;
+		const int nw = spec_rounds(t);
+		if (nw >= 2) return -nw;
 		int r = 256;
 		while (r < 2 * (4 * t.bw) + 66 && r < 2048) r <<= 1;    /* room for two in-kernel doublings */
 		while (r < 2 * t.bw + 66) r <<= 1;
@@ -529,8 +658,13 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 			SswTbTask& t = tasks[active[k]];
 			const int ring = ring_of(t);
 			size_t bw_last = (size_t)t.bw;                          /* widest band the kernel may reach by itself */
-			if (ring) while (2 * (2 * bw_last) + 66 <= (size_t)ring && 2 * bw_last <= (size_t)std::max(t.ref_len, t.read_len)) bw_last *= 2;
-			const size_t d = ((2 * bw_last + 1) * (size_t)t.read_len + 2 + 15) / 16 * 16;
+			if (ring > 0) while (2 * (2 * bw_last) + 66 <= (size_t)ring && 2 * bw_last <= (size_t)std::max(t.ref_len, t.read_len)) bw_last *= 2;
+			size_t d = ((2 * bw_last + 1) * (size_t)t.read_len + 2 + 15) / 16 * 16;
+			if (ring < 0) {                                         /* speculative kernel: every round has its own direction cells */
+				d = 0;
+				int b2 = t.bw;
+				for (int w = 0; w < -ring; ++w) { d += ssw_tb_dir_bytes(b2, t.read_len); b2 *= 2; }
+			}
 			const size_t r = ring ? 0 : 4 * ((size_t)t.ref_len + 2);
 			const size_t c = (size_t)t.ref_len + (size_t)t.read_len + 4;
 			const size_t need = dir_bytes + d + 4 * (row_ints + r) + 4 * (cig_words + c) + sizeof(SswTbTask) * (batch.size() + 1) + 1024;
@@ -567,7 +701,18 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 				st = side[si];
 			}
 			const dim3 grid((cnt + SSW_TB_WARPS - 1) / SSW_TB_WARPS);
-			if (ring) {
+			if (ring < 0) {
+				const int nw = -ring;
+				size_t smem = 0;
+				for (size_t x = g0; x < g1; ++x) {
+					size_t ints = (size_t)(n * n + 15) / 16 * 4;
+					int b2 = bt[x].bw;
+					for (int w = 0; w < nw; ++w) { ints += 4 * (size_t)ssw_tb_ring_of(b2); b2 *= 2; }
+					smem = std::max(smem, ints * sizeof(int32_t));
+				}
+				if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(ssw_banded_spec_kernel<0>), smem)) return -1;
+				ssw_launch(ssw_banded_spec_kernel<0>, dim3((unsigned)cnt), dim3(nw * 32), smem, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE, base, d_cig, nw);
+			} else if (ring) {
 				const size_t smem = (size_t)SSW_TB_WARPS * 4 * (size_t)ring * sizeof(int32_t) + (size_t)n * n + 16;
 				if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(ssw_banded_smem_kernel), smem)) return -1;
 				ssw_launch(ssw_banded_smem_kernel, grid, dim3(SSW_TB_THREADS), smem, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE, base, d_cig, ring);

@@ -107,6 +107,8 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
     L = _pkg()
     eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
     eng.set_option("latency_cols", 0)          # batch layouts (options are per engine)
+    eng.set_option("tb_spec", 0)               # band-doubling rounds one after the other: the emulator runs warps serially, and the
+                                               # side-by-side rounds are covered by the random and wide-band cases
     eng.set_option("super", 256)
     rng = np.random.default_rng(515)
     mat = C.dna_matrix(2, 2)
