@@ -66,7 +66,7 @@ struct SswOptions {
 	int64_t latency_cols = 1 << 20; /* "latency_cols": passes over at most this many reference columns use the 32-lane instances */
 	int force_inst = -1;            /* "inst" (measurements): use this forward instance whenever it covers the query */
 	int tb_maxbw = SSW_TBP_MAXBW;   /* "tb_maxbw": widest band handled by the shared-memory traceback kernel */
-	int tb_spec = 1;                /* "tb_spec": 1 = band-doubling rounds of a task side by side (speculative kernel), 0 = one after the other */
+	int tb_spec = -1;               /* "tb_spec": 1 = band-doubling rounds of a task side by side (speculative kernel), 0 = one after the other, -1 = automatic (small batches) */
 	int cm_block = -1;              /* "cm_block": -1 automatic, 0 one word per column always, 1 block maxima wherever chunking is possible (tests) */
 	int64_t chunk = 0;              /* "chunk": reference chunk length of the fill kernel (0 automatic) */
 	int64_t small_chunk = 0;        /* "small_chunk" (measurements): chunk length of launches too small to fill the device */
@@ -339,7 +339,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!strcmp(name, "grid_min")) { o.grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
 	if (!strcmp(name, "inst")) { o.force_inst = (int)value; return 0; }       /* index into kInst */
 	if (!strcmp(name, "super")) { o.strip_super = value >= 64 ? (int)(value + 7) / 8 * 8 : SSW_STRIP_SUPER; return 0; }
-	if (!strcmp(name, "tb_spec")) { o.tb_spec = value ? 1 : 0; return 0; }
+	if (!strcmp(name, "tb_spec")) { o.tb_spec = value < 0 ? -1 : (value ? 1 : 0); return 0; }
 	if (!strcmp(name, "tb_maxbw")) { o.tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;

@@ -607,7 +607,8 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
                              const int8_t* d_q, const int8_t* d_r, const int8_t* d_mat, int n, int gapO, int gapE,
                              SswDevBuf* scratch, float* ms_acc, int64_t* launches,
                              int tb_maxbw /* "tb_maxbw" option: bands above this use the global-memory kernel (tests: 0) */,
-                             int tb_spec /* "tb_spec" option: 0 = band-doubling rounds one after the other (no speculative kernel) */,
+                             int tb_spec /* "tb_spec" option: 0 = band-doubling rounds one after the other, 1 = side by side (speculative kernel),
+                                            -1 = side by side when the batch is too small to keep the device busy anyway */,
                              const std::function<int(size_t, const uint32_t*, int32_t, int)>& emit)
 {
 	std::vector<size_t> active(tasks.size());
@@ -623,8 +624,12 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 	/* Rounds of band doubling run side by side by the speculative kernel (1: not used).  Narrow bands (up to four tiles per row)
 	 * cost one tile latency per row whatever their width, so all of them go together; of wider ones at most two, so that
 	 * a task that needs only the first loses little. */
-	auto spec_rounds = [tb_maxbw, tb_spec](const SswTbTask& t) -> int {
-		if (!tb_spec) return 1;
+	/* Measured on a B200 (config 5, 1,000 reads of 10 kbp): with a thousand tasks in flight the phase is bound by instruction
+	 * issue, not by the latency of a row, and the speculative rounds make it slower (74 -> 86 ms); a single 10 kbp read
+	 * (one ssw_align call) is pure latency and gains.  Automatic: on for small batches only. */
+	const bool spec_on = tb_spec > 0 || (tb_spec < 0 && tasks.size() <= 256);
+	auto spec_rounds = [tb_maxbw, spec_on](const SswTbTask& t) -> int {
+		if (!spec_on) return 1;
 		const int len = std::max(t.ref_len, t.read_len);
 		int nw = 0, bw = t.bw;
 		while (nw < SSW_TBS_MAXW && bw <= tb_maxbw) {

@@ -137,7 +137,8 @@ int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t);
  *   "slices"        long-read CIGAR batches cut into slices on helper engines: 0 automatic, 1 never, 2 / 3 forced
  *   "grid_min"      smallest full score-only grid that is planned on the device
  *   "tb_maxbw"      widest band handled by the shared-memory traceback kernel
- *   "tb_spec"       1 (default): the band-doubling rounds of a traceback run side by side; 0: one after the other
+ *   "tb_spec"       band-doubling rounds of a traceback: 1 side by side (one warp per round), 0 one after the other,
+ *                   -1 (default) side by side for batches too small to keep the device busy
  */
 int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value);
 

@@ -1,5 +1,6 @@
 /* tools/call_bench.c -- latency and concurrency of the one-pair drop-in call from C, for any implementation of ssw.h.
- *   call_bench LIB.so n_calls threads ref_len read_len flag
+ *   call_bench LIB.so n_calls threads ref_len read_len flag [option=value ...]
+ * (options: ssw_engine_set_option(NULL, ...) of our library, e.g. tb_spec=0; ignored for libraries without that symbol)
  * Every call is ssw_init + ssw_align + align_destroy + init_destroy on the same (read, reference) pair, as a legacy
  * caller looping over reads does (main.c:462-532).  Prints microseconds per call for one thread and the wall time of
  * the same number of calls spread over `threads` pthreads (the reference is re-entrant; so is our engine pool). */
@@ -42,12 +43,26 @@ int main(int argc, char** argv)
 	if (!h) { fprintf(stderr, "%s\n", dlerror()); return 1; }
 	p_init = (fn_init)dlsym(h, "ssw_init"); p_idestroy = (fn_idestroy)dlsym(h, "init_destroy");
 	p_align = (fn_align)dlsym(h, "ssw_align"); p_adestroy = (fn_adestroy)dlsym(h, "align_destroy");
+	typedef int (*fn_opt)(void*, const char*, long long);
+	fn_opt p_opt = (fn_opt)dlsym(h, "ssw_engine_set_option");
+	for (int a = 7; a < argc && p_opt; ++a) {
+		char name[64]; long long v = 0;
+		if (sscanf(argv[a], "%63[^=]=%lld", name, &v) == 2) p_opt(NULL, name, v);
+	}
 	const int n = atoi(argv[2]), threads = atoi(argv[3]);
 	g_ref_len = atoi(argv[4]); g_read_len = atoi(argv[5]); g_flag = atoi(argv[6]);
 	g_ref = (int8_t*)malloc((size_t)g_ref_len); g_read = (int8_t*)malloc((size_t)g_read_len);
 	uint32_t x = 12345;
 	for (int i = 0; i < g_ref_len; ++i) { x = x * 1664525u + 1013904223u; g_ref[i] = (int8_t)((x >> 24) & 3); }
-	for (int i = 0; i < g_read_len; ++i) { x = x * 1664525u + 1013904223u; g_read[i] = ((x >> 20) % 10) ? g_ref[g_ref_len / 3 + i] : (int8_t)((x >> 24) & 3); }
+	/* the read: a copy of a stretch of the reference with ~5 % substitutions and ~2 % insertions / deletions */
+	for (int i = 0, rp = g_ref_len / 3; i < g_read_len; ++i) {
+		x = x * 1664525u + 1013904223u;
+		const unsigned u = (x >> 12) % 100;
+		if (u < 2 && g_read_len > 1000) { ++rp; }                                         /* deletion */
+		if (u >= 2 && u < 4 && g_read_len > 1000) { g_read[i] = (int8_t)((x >> 24) & 3); continue; }   /* insertion */
+		g_read[i] = (u < 9) ? (int8_t)((x >> 24) & 3) : g_ref[rp % g_ref_len];
+		++rp;
+	}
 	for (int i = 0; i < 25; ++i) g_mat[i] = (i / 5 == 4 || i % 5 == 4) ? 0 : (i / 5 == i % 5 ? 2 : -2);
 	/* warm-up: creates engines / scratch */
 	g_calls = 8;

@@ -318,6 +318,109 @@ __global__ void probe_body(uint32_t* out, long long* cyc, uint32_t seed)
 	if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// Reference-letter fetch A/B (north_star: "reference bases streamed from HBM with coalesced 128-bit loads"; the shipped kernel
+// issues one LDG.U8 per lane and step, served by L1).  The shipped cell formulation with
+//   LOADV 0: one byte load per step (as shipped)
+//   LOADV 1: one 64-bit load per 8 steps + a byte extract per step (PRMT/SHF on the ALU pipe -- the busy one)
+//   LOADV 2: one 128-bit load per 16 steps + byte extracts
+template <int R, int LOADV>
+__global__ void probe_letters(uint32_t* out, long long* cyc, uint32_t seed, const uint8_t* __restrict__ refbuf)
+{
+	__shared__ __align__(16) uint32_t prof[5 * 32 * R];
+	const int lane = threadIdx.x & 31;
+	for (int i = threadIdx.x; i < 5 * 32 * R; i += blockDim.x) {
+		const int v = (int)((seed * (i + 3)) % 5) - 2;
+		prof[i] = ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16);
+	}
+	__syncthreads();
+	uint32_t Hd[R], E[R];
+#pragma unroll
+	for (int k = 0; k < R; ++k) { Hd[k] = 0; E[k] = 0; }
+	uint32_t negO = 0xfffdfffdu, negE = 0xffffffffu, keep = lane == 0 ? 0u : 1u;
+	asm volatile("" : "+r"(negO), "+r"(negE), "+r"(keep));
+	uint32_t outH = 0, outF = 0, outC = 0, best = 0;
+	const uint8_t* lp = refbuf + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) / 8 * 4096 + 16 * (7 - (lane & 7));   // per-group window, 16-byte aligned
+	long long t0 = clock64();
+#pragma unroll 1
+	for (int it = 0; it < ITERS; it += 16) {
+		uint4 w4 = make_uint4(0, 0, 0, 0);
+		if (LOADV == 2) w4 = *reinterpret_cast<const uint4*>(lp + (it & 2047));
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			uint2 w2 = make_uint2(0, 0);
+			if (LOADV == 1) w2 = *reinterpret_cast<const uint2*>(lp + ((it + 8 * h) & 2047));
+			if (LOADV == 2) w2 = h ? make_uint2(w4.z, w4.w) : make_uint2(w4.x, w4.y);
+#pragma unroll
+			for (int u = 0; u < 8; ++u) {
+				const uint32_t inH = __shfl_up_sync(0xffffffffu, outH, 1) * keep;
+				uint32_t F = __shfl_up_sync(0xffffffffu, outF, 1) * keep;
+				const uint32_t inC = __shfl_up_sync(0xffffffffu, outC, 1) * keep;
+				int letter;
+				if (LOADV == 0) letter = (int)lp[(it + 8 * h + u) & 2047];
+				else letter = (int)(((u < 4 ? w2.x : w2.y) >> (8 * (u & 3))) & 0xffu);
+				uint32_t s[R], Hn[R];
+#pragma unroll
+				for (int q = 0; q < R / 4; ++q) {
+					const uint4 v = *reinterpret_cast<const uint4*>(&prof[letter * 32 * R + q * 128 + lane * 4]);
+					s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+				}
+#pragma unroll
+				for (int k = 0; k < R; ++k) {
+					const uint32_t X = __viaddmax_s16x2_relu(Hd[k], s[k], E[k]);
+					const uint32_t Xg = __vadd2(X, negO);
+					E[k] = __viaddmax_s16x2(E[k], negE, Xg);
+					Hn[k] = __vmaxs2(X, F);
+					F = __viaddmax_s16x2(F, negE, Xg);
+				}
+				uint32_t m = __vimax3_s16x2(Hn[0], Hn[1], Hn[2]);
+#pragma unroll
+				for (int k = 3; k + 1 < R; k += 2) m = __vimax3_s16x2(m, Hn[k], Hn[k + 1]);
+				if (((R - 3) & 1) != 0) m = __vmaxs2(m, Hn[R - 1]);
+				outC = __vmaxs2(m, inC);
+				const uint32_t nb = __vmaxs2(best, m);
+				if (nb != best) best = nb;
+				Hd[0] = inH;
+#pragma unroll
+				for (int k = 1; k < R; ++k) Hd[k] = Hn[k - 1];
+				outH = Hn[R - 1];
+				outF = F;
+			}
+		}
+	}
+	long long t1 = clock64();
+	uint32_t acc = best ^ outC ^ outF;
+#pragma unroll
+	for (int k = 0; k < R; ++k) acc ^= E[k] ^ Hd[k];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+	if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <class K>
+static double run_letters(K kern, int threads, int sms)
+{
+	uint32_t* out; long long* cyc; uint8_t* refbuf;
+	const size_t ref_bytes = (size_t)sms * threads / 8 * 4096 + 8192;
+	cudaMalloc(&out, sizeof(uint32_t) * threads * sms);
+	cudaMalloc(&cyc, sizeof(long long) * sms);
+	cudaMalloc(&refbuf, ref_bytes);
+	uint8_t* h = new uint8_t[ref_bytes];
+	uint32_t x = 777;
+	for (size_t i = 0; i < ref_bytes; ++i) { x = x * 1664525u + 1013904223u; h[i] = (uint8_t)((x >> 24) & 3); }
+	cudaMemcpy(refbuf, h, ref_bytes, cudaMemcpyHostToDevice);
+	delete[] h;
+	kern<<<sms, threads>>>(out, cyc, 12345u, refbuf);
+	kern<<<sms, threads>>>(out, cyc, 12345u, refbuf);
+	cudaDeviceSynchronize();
+	long long* hc = new long long[sms];
+	cudaMemcpy(hc, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+	double avg = 0;
+	for (int i = 0; i < sms; ++i) avg += (double)hc[i];
+	avg /= sms;
+	delete[] hc;
+	cudaFree(out); cudaFree(cyc); cudaFree(refbuf);
+	return (double)(threads / 32) * ITERS / avg;          // warp-steps per clock per SM
+}
+
 template <class K>
 static double run(K kern, int threads, int ops_per_iter, int sms, uint32_t seed = 12345u)
 {
@@ -400,6 +503,11 @@ int main()
 				const double k = 32.0 * 2.0 * 20.0 * sms * (clk_khz * 1e3) / 1e9;
 				const double b0 = run(probe_body<20, 0>, thr, 1, sms), b1 = run(probe_body<20, 1>, thr, 1, sms), b2 = run(probe_body<20, 2>, thr, 1, sms);
 				printf(", \"fill_body_R20_%dthr_gcups\": {\"shipped: 5 ALU per cell pair\": %.1f, \"biased: 4 ALU + 2 IMAD\": %.1f, \"biased: 4 ALU + 4 IMAD\": %.1f}", thr, b0 * k, b1 * k, b2 * k);
+			}
+			{
+				const double k = 32.0 * 2.0 * 20.0 * sms * (clk_khz * 1e3) / 1e9;
+				printf(", \"letter_fetch_R20_512thr_gcups\": {\"LDG.U8 per step (shipped)\": %.1f, \"LDG.64 per 8 steps + byte extract\": %.1f, \"LDG.128 per 16 steps + byte extract\": %.1f}",
+				       run_letters(probe_letters<20, 0>, 512, sms) * k, run_letters(probe_letters<20, 1>, 512, sms) * k, run_letters(probe_letters<20, 2>, 512, sms) * k);
 			}
 			const double cells_per_clk_sm = r[0] * 32.0 * 2.0 / 5.5;
 			printf(", \"gcups_peak_5p5_ops_per_cellpair\": %.1f", cells_per_clk_sm * sms * (clk_khz * 1e3) / 1e9);
