@@ -663,8 +663,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 	constexpr int R = SSW_STRIP_R;
 	Trace tr;
 	const int rows_per_strip = 32 * R;
-	const size_t warp_smem = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t) + ssw_snap_smem_bytes<R>(32);      /* profile + best-cell snapshots of one warp */
-	const size_t warp_prof = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t);
+	const size_t warp_smem = (size_t)(P.n + 1) * 32 * R * sizeof(uint32_t);
 	/* one launch per distinct strip count (it fixes the CTA shape) */
 	std::vector<size_t> order(reqs.size());
 	for (size_t i = 0; i < reqs.size(); ++i) order[i] = i;
@@ -766,7 +765,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		gsync[0] = 0;
 		if (e->d_sync.ensure(sizeof(int) * gsync.size())) return -1;
 		SSW_CUDA_OK(cudaMemcpyAsync(e->d_sync.p, gsync.data(), sizeof(int) * gsync.size(), cudaMemcpyHostToDevice, e->stream));
-		const size_t smem = (size_t)nw * warp_prof + sizeof(int) * (size_t)((n_strips + 2 + 3) / 4 * 4) + ssw_snap_smem_bytes<R>(nw * 32);
+		const size_t smem = (size_t)nw * warp_smem + sizeof(int) * (size_t)(n_strips + 4);
 		tr.lap("strips: h2d + memset");
 		e->laps.start(e->stream);
 #define SSW_STRIPS_GO(DIR, TERM, SPLIT)                                                                                 \

@@ -206,33 +206,51 @@ struct SswLaneBest {
  * running maximum grows with every column and some lane of a warp has an event on almost every step; a snapshot kept in
  * registers made the event 2R register moves (21 % of all executed instructions of the config-4 kernel in round 1,
  * profiles/ncu_fill_cfg4_r1.txt). */
-template <int R>
+template <int R, bool SMEM = true>
 struct SswSnap {
 	uint4* base;        /* this thread's slots: (h, q) is base[h * Q + q] */
 	static constexpr int Q = (R + 3) / 4;
+};
+/* Register variant (the strip-pipelined kernel: 10 rows per lane, one CTA per SM whatever its shared memory; measured 3-5 %
+ * faster there than the shared-memory snapshot, which needs 127 registers in the split variant). */
+template <int R>
+struct SswSnap<R, false> {
+	uint32_t w[2][R];
 };
 template <int R>
 static inline size_t ssw_snap_smem_bytes(int threads) { return (size_t)(2 * ((R + 3) / 4) + 1) * (size_t)threads * sizeof(uint4); }
 
 template <int R>
-__device__ static __forceinline__ void ssw_snap_init(SswSnap<R>& sn, uint4* area, int tid)
+__device__ static __forceinline__ void ssw_snap_init(SswSnap<R, true>& sn, uint4* area, int tid)
 {
-	sn.base = area + (size_t)tid * (2 * SswSnap<R>::Q + 1);
+	sn.base = area + (size_t)tid * (2 * SswSnap<R, true>::Q + 1);
 #pragma unroll
-	for (int i = 0; i < 2 * SswSnap<R>::Q; ++i) sn.base[i] = make_uint4(0, 0, 0, 0);
+	for (int i = 0; i < 2 * SswSnap<R, true>::Q; ++i) sn.base[i] = make_uint4(0, 0, 0, 0);
+}
+template <int R>
+__device__ static __forceinline__ void ssw_snap_init(SswSnap<R, false>& sn)
+{
+#pragma unroll
+	for (int k = 0; k < R; ++k) { sn.w[0][k] = 0; sn.w[1][k] = 0; }
 }
 
 template <int R>
-__device__ static __forceinline__ void ssw_snap_store(const SswSnap<R>& sn, int h, const uint32_t (&Hn)[R])
+__device__ static __forceinline__ void ssw_snap_store(const SswSnap<R, true>& sn, int h, const uint32_t (&Hn)[R])
 {
-	constexpr int Q = SswSnap<R>::Q;
+	constexpr int Q = SswSnap<R, true>::Q;
 #pragma unroll
 	for (int q = 0; q < Q; ++q)
 		sn.base[h * Q + q] = make_uint4(Hn[4 * q], 4 * q + 1 < R ? Hn[4 * q + 1] : 0u, 4 * q + 2 < R ? Hn[4 * q + 2] : 0u, 4 * q + 3 < R ? Hn[4 * q + 3] : 0u);
 }
-
 template <int R>
-__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, const SswSnap<R>& sn, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1)
+__device__ static __forceinline__ void ssw_snap_store(SswSnap<R, false>& sn, int h, const uint32_t (&Hn)[R])
+{
+#pragma unroll
+	for (int k = 0; k < R; ++k) sn.w[h][k] = Hn[k];
+}
+
+template <int R, bool SMEM>
+__device__ static __forceinline__ void ssw_track(SswLaneBest& lb, SswSnap<R, SMEM>& sn, uint32_t nb, const uint32_t (&Hn)[R], int sp, int p0, int p1)
 {
 #ifndef SSW_CPU_EMU
 	asm volatile("" : "+r"(sp));                /* keep the range test inside this path */
@@ -246,9 +264,9 @@ __device__ static __forceinline__ void ssw_track(SswLaneBest& lb, const SswSnap<
 
 /* after the sweep: smallest row of this lane that held the lane's best value when it was recorded */
 template <int R>
-__device__ static __forceinline__ void ssw_track_rows(SswLaneBest& lb, const SswSnap<R>& sn, int row_base)
+__device__ static __forceinline__ void ssw_track_rows(SswLaneBest& lb, const SswSnap<R, true>& sn, int row_base)
 {
-	constexpr int Q = SswSnap<R>::Q;
+	constexpr int Q = SswSnap<R, true>::Q;
 	lb.row0 = SSW_NO_ROW; lb.row1 = SSW_NO_ROW;
 #pragma unroll
 	for (int q = Q - 1; q >= 0; --q) {
@@ -260,6 +278,16 @@ __device__ static __forceinline__ void ssw_track_rows(SswLaneBest& lb, const Ssw
 			if (half_of(wa[j], 0) == half_of(lb.best, 0)) lb.row0 = row_base + 4 * q + j;
 			if (half_of(wb[j], 1) == half_of(lb.best, 1)) lb.row1 = row_base + 4 * q + j;
 		}
+	}
+}
+template <int R>
+__device__ static __forceinline__ void ssw_track_rows(SswLaneBest& lb, const SswSnap<R, false>& sn, int row_base)
+{
+	lb.row0 = SSW_NO_ROW; lb.row1 = SSW_NO_ROW;
+#pragma unroll
+	for (int k = R - 1; k >= 0; --k) {
+		if (half_of(sn.w[0][k], 0) == half_of(lb.best, 0)) lb.row0 = row_base + k;
+		if (half_of(sn.w[1][k], 1) == half_of(lb.best, 1)) lb.row1 = row_base + k;
 	}
 }
 
@@ -559,12 +587,11 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 	const int s_first = part * per_part, s_last = min(T.n_strips, s_first + per_part);      /* this CTA's strips [s_first, s_last) */
 	volatile int* gprog_in = gsync + 1 + (SPLIT ? unit - 1 : 0);          /* published by the previous block of the same task */
 	volatile int* gprog_out = gsync + 1 + (SPLIT ? unit : 0);
-	/* shared memory: NW profiles, then prog[n_strips], the stop flag and the done bits, then (16-byte aligned) the snapshot area */
+	/* shared memory: NW profiles, then prog[n_strips], the stop flag and the done bits */
 	uint32_t* prof = smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
 	volatile int* prog = reinterpret_cast<volatile int*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R);
 	volatile int* stop = prog + T.n_strips;                /* 1: every requested half has met its score (reverse pass) */
 	volatile int* done = stop + 1;                          /* bit h: half h has met its score */
-	uint4* snap_area = reinterpret_cast<uint4*>(smem + (size_t)NW * (size_t)(n + 1) * 32 * R + (size_t)((T.n_strips + 2 + 3) / 4 * 4));
 	const int need_mask = (T.term_a >= 0 ? 1 : 0) | (T.term_b >= 0 ? 2 : 0);
 	for (int i = threadIdx.x; i < T.n_strips; i += blockDim.x) prog[i] = -0x40000000;
 	if (threadIdx.x == 0) { *stop = 0; *done = 0; }
@@ -605,8 +632,8 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 			}
 			SswLaneBest lb;
 			lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
-			SswSnap<R> snap;
-			ssw_snap_init<R>(snap, snap_area, (int)threadIdx.x);
+			SswSnap<R, false> snap;
+			ssw_snap_init<R>(snap);
 
 			const uint32_t* bin = bnd + T.bnd_off + (size_t)((s + 1) & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;   /* written by strip s-1 */
 			uint32_t* bout = bnd + T.bnd_off + (size_t)(s & 1) * 3 * T.bnd_len + SSW_STRIP_BPAD;
