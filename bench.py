@@ -417,7 +417,7 @@ def main():
     cores = C.effective_cores()[0]
 
     # ---- headline: config 3, strong-scaled ----
-    tiny = dict(ref_len=3000, read_len=60) if X.emu else {}
+    tiny = dict(ref_len=2000, read_len=60) if X.emu else {}
     W3 = C.config_workload(3, n_reads=args.reads, **tiny)
     sampler = {"smi": ClockSampler, "nvml": NvmlSampler}[args.clock_sampler](X.local)
     st3, got3 = run_shape(X, 3, W3, args.steps, args.warmup, args.e2e_reps, sampler)
@@ -474,7 +474,7 @@ def main():
     # ---- sub-results: the other named shapes, same natural split ----
     subs = {}
     if 2 in only:
-        W = C.config_workload(2, **(dict(n_reads=10, **tiny) if X.emu else {}))
+        W = C.config_workload(2, **(dict(n_reads=4, **tiny) if X.emu else {}))
         st, got = run_shape(X, 2, W, max(args.sub_steps, 3), 3, args.e2e_reps)
         if rank0:
             o = sub_result(st, X.world, "config2", "1,000 x 150 bp reads vs 5 Mbp, byte-score path, flag 0 (strong: reads split over the GPUs)")
@@ -503,7 +503,7 @@ def main():
             subs["config4"] = o
         del got
     if 5 in only:
-        W = C.config_workload(5, **(dict(n_reads=6, ref_len=2000, read_len=400) if X.emu else {}))
+        W = C.config_workload(5, **(dict(n_reads=3, ref_len=1500, read_len=330) if X.emu else {}))
         st, got = run_shape(X, 5, W, args.sub_steps, 2, args.e2e_reps)
         if rank0:
             o = sub_result(st, X.world, "config5", "1,000 x 10 kbp reads vs 100 kbp, byte pass overflows -> word path, flag 2 (begin search + banded traceback, "

@@ -230,6 +230,9 @@ __device__ static __forceinline__ void ssw_snap_init(SswSnap<R, true>& sn, uint4
 template <int R>
 __device__ static __forceinline__ void ssw_snap_init(SswSnap<R, false>& sn)
 {
+#ifndef SSW_CPU_EMU
+	asm volatile("" : : "l"(&sn) : "memory");       /* as in round 1: lets the compiler keep the snapshot out of the hot registers */
+#endif
 #pragma unroll
 	for (int k = 0; k < R; ++k) { sn.w[0][k] = 0; sn.w[1][k] = 0; }
 }

@@ -34,14 +34,14 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and d["config"]["workload"].startswith("config3")
 
 
-DRY = ["--dry-run-emu", "--reads", "13", "--steps", "1", "--warmup", "1", "--c4-queries", "5", "--c4-targets", "9", "--parity", "13",
+DRY = ["--dry-run-emu", "--reads", "7", "--steps", "1", "--warmup", "1", "--c4-queries", "3", "--c4-targets", "5", "--parity", "7",
        "--e2e-reps", "1", "--sub-steps", "1"]
 
 
 def _check_b200_line(d, world):
     for k in BASE_KEYS + ("clocks", "gpu_launches", "roofline", "alu_roofline", "parity", "parity_checked", "mismatches", "config2", "config4", "config5"):
         assert k in d, k
-    assert d["n_gpus"] == world and d["scaling"] == "strong" and d["mismatches"] == 0 and d["parity_checked"] >= 13 + 10 + 45 + 6
+    assert d["n_gpus"] == world and d["scaling"] == "strong" and d["mismatches"] == 0 and d["parity_checked"] >= 7 + 4 + 15 + 3
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     for c in ("config2", "config4", "config5"):
         assert {"value", "e2e", "phases_ms", "alu_roofline", "parity"} <= set(d[c]) and d[c]["parity"]["mismatches"] == 0
