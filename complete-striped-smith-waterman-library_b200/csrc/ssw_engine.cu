@@ -63,6 +63,8 @@ struct SswOptions {
 	int strip_parts = 0;            /* "parts": 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
 	int strip_super = SSW_STRIP_SUPER;   /* "super": columns per super-block of the strip kernel (tests) */
 	int grid_min_pairs = 32768;     /* "grid_min": smaller grids use the general path */
+	int64_t grid_split_pairs = (int64_t)4 << 20;   /* "grid_split": grids of at least this many pairs are cut into launch groups whose records are copied back while the next group computes */
+	int grid_group_qp = 16;         /* "grid_group": smallest such group, in query pairs */
 	int64_t latency_cols = 1 << 20; /* "latency_cols": passes over at most this many reference columns use the 32-lane instances */
 	int force_inst = -1;            /* "inst" (measurements): use this forward instance whenever it covers the query */
 	int tb_maxbw = SSW_TBP_MAXBW;   /* "tb_maxbw": widest band handled by the shared-memory traceback kernel */
@@ -119,6 +121,17 @@ struct ssw_engine {
 	ssw_engine_timing timing;
 	SswTimer t_total;
 	SswLaps laps;                    /* per-phase kernel times, read once at the end of a call */
+	std::vector<cudaEvent_t> grid_events;    /* one per launch group of the device-planned grid (records are copied back behind it) */
+	int grid_event(size_t i, cudaEvent_t* out)
+	{
+		while (grid_events.size() <= i) {
+			cudaEvent_t ev = nullptr;
+			if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return -1;
+			grid_events.push_back(ev);
+		}
+		*out = grid_events[i];
+		return 0;
+	}
 
 	int upload_refs(int n);
 	int run_fill(const std::vector<SswItem>& items, int inst, int dir, int cm_mode, int share, const ssw_batch_params& P, float* ms_acc);
@@ -317,6 +330,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 	for (ssw_engine*& k : e->kids) if (k) { ssw_engine_destroy(k); k = nullptr; }
 	e->staged.release();
 	for (cudaStream_t& st : e->side) if (st) { cudaStreamDestroy(st); st = nullptr; }
+	for (cudaEvent_t ev : e->grid_events) if (ev) cudaEventDestroy(ev);
 	if (e->stream) cudaStreamDestroy(e->stream);
 	--ssw_live_engines();
 	delete e;
@@ -336,6 +350,8 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!strcmp(name, "chunk")) { o.chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "cm_block")) { o.cm_block = value < 0 ? -1 : (value ? 1 : 0); return 0; }
 	if (!strcmp(name, "cm_budget_mb")) { o.cm_budget = value <= 0 ? 0 : value << 20; return 0; }
+	if (!strcmp(name, "grid_split")) { o.grid_split_pairs = value < 0 ? (int64_t)4 << 20 : value; return 0; }
+	if (!strcmp(name, "grid_group")) { o.grid_group_qp = value < 1 ? 16 : (int)value; return 0; }
 	if (!strcmp(name, "grid_min")) { o.grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
 	if (!strcmp(name, "inst")) { o.force_inst = (int)value; return 0; }       /* index into kInst */
 	if (!strcmp(name, "super")) { o.strip_super = value >= 64 ? (int)(value + 7) / 8 * 8 : SSW_STRIP_SUPER; return 0; }
@@ -1258,6 +1274,8 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 	const size_t free_b = ssw_free_device_bytes();
 	const size_t budget = std::max<size_t>((size_t)256 << 20, ssw_budget_share(free_b + e->d_colmax.cap + e->d_items.cap + e->d_alns.cap + e->d_res.cap));
 	tr.lap("grid: tables");
+	struct GridGroup { cudaEvent_t ev; int32_t q_lo, q_n; bool contiguous; };
+	std::vector<GridGroup> groups;
 	size_t k = 0;
 	while (k < order.size()) {
 		const int inst = q_inst[order[k]];
@@ -1265,8 +1283,13 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		const int n_r_pad = (n_r + per_cta - 1) / per_cta * per_cta;
 		/* query pairs of this launch: same instance, bounded by memory */
 		const size_t per_qp = (size_t)cm_per_qp * 4 + (size_t)n_r_pad * (sizeof(SswItem) + sizeof(SswItemBest)) + (size_t)n_r * 2 * (sizeof(SswAlnDesc) + sizeof(SswFillResult));
-		const size_t max_qp = std::max<size_t>(1, budget / per_qp);
+		size_t max_qp = std::max<size_t>(1, budget / per_qp);
+		/* large grids: several launch groups even when memory would allow one, so that the records of a finished group are
+		 * copied to the host while the next group computes (115 MB of records per million pairs) */
+		if ((int64_t)n_q * n_r >= e->opt.grid_split_pairs)
+			max_qp = std::min<size_t>(max_qp, std::max<size_t>((size_t)std::max(e->opt.grid_group_qp, 1), ((size_t)n_q / 2 + 7) / 8));
 		std::vector<int2> qps;
+		const size_t k_first = k;
 		while (k < order.size() && q_inst[order[k]] == inst && qps.size() < max_qp) {
 			int2 pr = make_int2(order[k], -1);
 			++k;
@@ -1315,11 +1338,29 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		}
 		e->laps.stop(e->stream, &e->timing.resolve_ms);
 		e->timing.other_launches += 2;
+		/* the group's records are final once its emit kernel has run: remember the event and, when the group's queries are a
+		 * contiguous ascending range (equal-length queries: `order` is the identity), the slice of records they own */
+		GridGroup gg;
+		if (e->grid_event(groups.size(), &gg.ev)) return -1;
+		SSW_CUDA_OK(cudaEventRecord(gg.ev, e->stream));
+		gg.q_lo = order[k_first]; gg.q_n = (int32_t)(k - k_first); gg.contiguous = true;
+		for (size_t i = k_first; i < k; ++i) if (order[i] != gg.q_lo + (int32_t)(i - k_first)) gg.contiguous = false;
+		groups.push_back(gg);
 		tr.lap("grid: launch group");
 	}
+	/* every launch is queued; bring the records back group by group on the copy stream while later groups still compute */
+	bool all_contiguous = !groups.empty();
+	for (const GridGroup& gg : groups) if (!gg.contiguous) all_contiguous = false;
+	if (all_contiguous && groups.size() > 1) {
+		if (!e->side[0]) SSW_CUDA_OK(cudaStreamCreateWithFlags(&e->side[0], cudaStreamNonBlocking));
+		for (const GridGroup& gg : groups) {
+			SSW_CUDA_OK(cudaStreamWaitEvent(e->side[0], gg.ev, 0));
+			const size_t first = (size_t)gg.q_lo * (size_t)n_r, cnt = (size_t)gg.q_n * (size_t)n_r;
+			if (e->staged.copy(results + first, e->d_out.as<ssw_batch_result>() + first, sizeof(ssw_batch_result) * cnt, e->side[0])) return -1;
+		}
+	} else if (e->staged.copy(results, e->d_out.p, sizeof(ssw_batch_result) * (size_t)n_pairs, e->stream)) return -1;
 	int32_t n_redo = 0;
 	SSW_CUDA_OK(cudaMemcpyAsync(&n_redo, gb + o_cnt, 4, cudaMemcpyDeviceToHost, e->stream));
-	if (e->staged.copy(results, e->d_out.p, sizeof(ssw_batch_result) * (size_t)n_pairs, e->stream)) return -1;
 	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
 	if (n_redo > redo_cap) {                     /* more overflows than the list holds: find them by scanning is not possible -> general path */
 		return 0;

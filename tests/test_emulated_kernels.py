@@ -246,12 +246,22 @@ def test_emulated_device_planned_grid(oracle, capfd):
             assert n_over > 0          # the high-identity 150-mers overflow 8-bit scores
     # protein grid (BLOSUM50, 24 letters): the CTA-shared profile is 64 KB, so the launch uses eight warps per CTA
     W = C.config_workload(4, n_queries=5, n_targets=37)
-    W["queries"][3] = W["queries"][3][:170]              # another kernel instance and a ragged grid
+    pq, pr = np.repeat(np.arange(5), 37), np.tile(np.arange(37), 5)
+    # equal-length queries, forced into launch groups of one query pair: the records come back group by group
+    eng.set_option("grid_split", 1)
+    eng.set_option("grid_group", 1)
     eng.set_sequences(W["queries"], W["refs"])
     res, pool = eng.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
-    pq, pr = np.repeat(np.arange(5), 37), np.tile(np.arange(37), 5)
     exp, exp_pool, _, _, _ = C.cpu_batch(W["queries"], W["refs"], pq, pr, C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1, threads=4)
     assert C.compare_records(res, pool, exp, exp_pool) == []
+    assert eng.timing()["fill_forward_launches"] == 3
+    W["queries"][3] = W["queries"][3][:170]              # another kernel instance and a ragged grid (groups not contiguous: one copy at the end)
+    eng.set_sequences(W["queries"], W["refs"])
+    res, pool = eng.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
+    exp, exp_pool, _, _, _ = C.cpu_batch(W["queries"], W["refs"], pq, pr, C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1, threads=4)
+    assert C.compare_records(res, pool, exp, exp_pool) == []
+    eng.set_option("grid_split", -1)
+    eng.set_option("grid_group", -1)
     eng.set_option("grid_min", -1)
     eng.close()
 

@@ -123,6 +123,19 @@ def test_config4_subgrid(engine, ref_lib, capfd):
               gapO=3, gapE=1, flag=0, filters=0, filterd=0, mask_len=150, score_size=1)
 
 
+def test_config4_grid_in_launch_groups(engine, ref_lib, capfd):
+    """96 queries x 50,000 targets = 4.8 M pairs: large enough for the device-planned grid to run as several launch groups whose
+    records are copied back while the next group computes; every pair against the compiled reference."""
+    W = C.config_workload(4, n_queries=96, n_targets=50_000)
+    engine.set_sequences(W["queries"], W["refs"])
+    res, pool = engine.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
+    assert engine.timing()["fill_forward_launches"] >= 3
+    pq = np.repeat(np.arange(96), 50_000)
+    pr = np.tile(np.arange(50_000), 96)
+    check_all("config4_launch_groups", capfd, res, pool, W["queries"], W["refs"], pq, pr, C.BLOSUM50, 24,
+              gapO=3, gapE=1, flag=0, filters=0, filterd=0, mask_len=150, score_size=1)
+
+
 @pytest.mark.parametrize("flag", [0x0f, 2])
 def test_config5_all_long_reads(engine, ref_lib, flag, capfd):
     ref, reads = _workload(100_000, 1000, 10_000, 5005, 5006, decoy_frac=0.0, p_sub=0.05, p_ins=0.02, p_del=0.02)
