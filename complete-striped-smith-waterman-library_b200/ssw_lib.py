@@ -185,8 +185,10 @@ class BatchAligner(object):
         self._lens = (ql, np.diff(ro))
 
     def align(self, mat, n, gap_open=3, gap_extend=1, flag=0, filters=0, filterd=0, mask_len=-1, score_size=2,
-              pair_query=None, pair_ref=None, want_cigar=None):
-        """Align pairs of the resident sequences; returns (results[RESULT_DTYPE], cigar_pool[uint32])."""
+              pair_query=None, pair_ref=None, want_cigar=None, out=None):
+        """Align pairs of the resident sequences; returns (results[RESULT_DTYPE], cigar_pool[uint32]).
+        out: a results array of a previous call with the same number of pairs to write into (large grids return
+        hundreds of MB of records; re-using the buffer avoids mapping and unmapping it on every call)."""
         mat, matp = _i8(mat)
         P = BatchParams(matp, n, gap_open, gap_extend, flag, filters, filterd, mask_len, score_size)
         if pair_query is None:
@@ -198,7 +200,10 @@ class BatchAligner(object):
             n_pairs = len(pq_a)
             pq = pq_a.ctypes.data_as(ct.POINTER(ct.c_int32))
             pr = pr_a.ctypes.data_as(ct.POINTER(ct.c_int32))
-        res = np.empty(n_pairs, dtype=RESULT_DTYPE)         # every record is written by the library
+        if out is not None and out.dtype == RESULT_DTYPE and len(out) == n_pairs and out.flags["C_CONTIGUOUS"]:
+            res = out
+        else:
+            res = np.empty(n_pairs, dtype=RESULT_DTYPE)     # every record is written by the library
         if want_cigar is None:
             want_cigar = bool(flag & 7)
         cap = 0
