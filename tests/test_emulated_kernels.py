@@ -485,3 +485,43 @@ def test_emulated_resident_reference_cache(emu, oracle, capfd):
     assert C.diff_results(emu.align(**kw), oracle.align(**kw)) == []
     kw = dict(read=reads[1], ref=ref, mat=mat, n=5, gapO=3, gapE=1, flag=8, filters=0, filterd=0, maskLen=20, score_size=2)
     assert C.diff_results(emu.align(**kw), oracle.align(**kw)) == []
+
+
+def test_emulated_argument_validation(capfd):
+    """The C ABI rejects malformed input with -1 instead of reading out of bounds, dividing by zero or letting a C++ exception
+    escape (round-1 advisor findings): decreasing offsets, offsets that do not start at 0, NULL offset arrays, a full grid over an
+    empty reference set, pair indices out of range; an empty batch is fine."""
+    import ctypes as ct
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    lib = eng.lib
+    I64P, I8P = ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int8)
+    q = np.array([0, 1, 2, 3, 0, 1, 2, 3], dtype=np.int8)
+    r = np.array([0, 1, 2, 3] * 8, dtype=np.int8)
+
+    def set_seq(nq, qoff, nr, roff):
+        qo = np.array(qoff, dtype=np.int64) if qoff is not None else None
+        ro = np.array(roff, dtype=np.int64) if roff is not None else None
+        return lib.ssw_engine_set_sequences(eng.h, nq, q.ctypes.data_as(I8P), qo.ctypes.data_as(I64P) if qo is not None else None,
+                                            nr, r.ctypes.data_as(I8P), ro.ctypes.data_as(I64P) if ro is not None else None)
+
+    assert set_seq(2, [0, 4, 8], 1, [0, 32]) == 0
+    assert set_seq(2, [0, 6, 4], 1, [0, 32]) == -1            # decreasing
+    assert set_seq(2, [1, 4, 8], 1, [0, 32]) == -1            # does not start at 0
+    assert set_seq(2, None, 1, [0, 32]) == -1                 # NULL offsets with sequences
+    assert set_seq(2, [0, 4, 8], 1, [0, -5]) == -1            # negative length
+    assert set_seq(2, [0, 4, 8], 0, None) == 0                # no references at all is a valid resident set ...
+    mat = C.dna_matrix(2, 2)
+    P = L.BatchParams(mat.ctypes.data_as(I8P), 5, 3, 1, 0, 0, 0, 15, 2)
+    res = np.zeros(4, dtype=L.RESULT_DTYPE)
+    used = ct.c_int64(0)
+    # ... but a grid over it is not
+    assert lib.ssw_engine_align(eng.h, ct.byref(P), 2, None, None, res.ctypes.data_as(ct.c_void_p), None, 0, ct.byref(used)) == -1
+    assert lib.ssw_engine_align(eng.h, ct.byref(P), 0, None, None, None, None, 0, ct.byref(used)) == 0
+    assert set_seq(2, [0, 4, 8], 1, [0, 32]) == 0
+    pq = np.array([0, 5], dtype=np.int32)
+    pr = np.array([0, 0], dtype=np.int32)
+    assert lib.ssw_engine_align(eng.h, ct.byref(P), 2, pq.ctypes.data_as(ct.POINTER(ct.c_int32)), pr.ctypes.data_as(ct.POINTER(ct.c_int32)),
+                                res.ctypes.data_as(ct.c_void_p), None, 0, ct.byref(used)) == -1
+    eng.close()
