@@ -635,10 +635,21 @@ static int run_resolve(ssw_engine* e, const std::vector<SswAlnDesc>& descs, bool
  * `refill` for a fill with the other row count.
  */
 static int resolve_forward(ssw_engine* e, std::vector<SswAlnDesc>& descs, const std::vector<int64_t>& desc_aln, std::vector<Aln>& alns,
-                           int word, const Sem& S, bool word_first, std::vector<int64_t>* refill, const CmMode* cm = nullptr)
+                           int word, const Sem& S, bool word_first, std::vector<int64_t>* refill, const CmMode* cm = nullptr, bool dual = false)
 {
 	std::vector<SswFillResult> res;
 	if (run_resolve(e, descs, true, res, cm)) return -1;
+	if (dual) {
+		/* descriptors come in pairs: (byte semantics, word semantics) of the same alignment, filled side by side in the two
+		 * halves of one pair-task.  The reference takes the byte result unless it overflowed (ssw.c:881-886). */
+		for (size_t i = 0; i + 1 < descs.size(); i += 2) {
+			Aln& a = alns[desc_aln[i]];
+			const bool over = res[i].overflow == 1;
+			a.fwd = over ? res[i + 1] : res[i];
+			a.word = over ? 1 : 0;
+		}
+		return 0;
+	}
 	std::vector<SswAlnDesc> alt;
 	std::vector<int64_t> alt_aln;
 	for (size_t i = 0; i < descs.size(); ++i) {
@@ -877,7 +888,15 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 	 * kernels for large grids.  rank[q] orders the distinct queries by (instance, padded length, id). */
 	struct PT { int inst; int64_t a, b; int32_t r, qa, qb; };
 	std::vector<PT> pts;
-	{
+	/* Latency path with both profiles (a one-pair ssw_align with score_size 2): half B of a lone alignment's pair-task is
+	 * idle, so it carries the SAME read with word semantics (other pad rows, other limit).  A read whose byte pass overflows
+	 * (ssw.c:883-886) then costs one fill instead of two -- for free. */
+	const bool dual = latency && word == 0 && !word_first && S.has_byte && S.has_word;
+	if (dual) {
+		std::sort(keys.begin(), keys.end(), by_ref);
+		pts.reserve(keys.size());
+		for (const Key& k : keys) { PT pt; pt.inst = k.inst; pt.a = k.idx; pt.b = k.idx; pt.r = k.r; pt.qa = k.q; pt.qb = k.q; pts.push_back(pt); }
+	} else {
 		std::vector<int32_t> qids;
 		qids.reserve(keys.size());
 		std::vector<int32_t> rank((size_t)e->n_q, -1), q_inst((size_t)e->n_q, 0);
@@ -964,7 +983,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				const Aln& A = alns[pt.a];
 				const Aln* B = pt.b >= 0 ? &alns[pt.b] : nullptr;
 				const int32_t ref_len = e->r_len[pt.r];
-				const int max_lp = std::max(lp_of(A.read_len, word), B ? lp_of(B->read_len, word) : 0);
+				const int max_lp = std::max(lp_of(A.read_len, word), B ? lp_of(B->read_len, dual ? 1 : word) : 0);
 				const int max_len = std::max(A.read_len, B ? B->read_len : 0);
 				/* a path with positive score spans at most max_lp diagonal steps plus (total positive score)/gapE gap columns */
 				int64_t warm = 0, chunk = ref_len;
@@ -1033,7 +1052,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 			SswItem it;
 			memset(&it, 0, sizeof(it));
 			it.qa.off = (int32_t)e->q_off[A.q]; it.qa.len = A.read_len; it.qa.lp = lp_of(A.read_len, word); it.qa.rev = 0;
-			if (B) { it.qb.off = (int32_t)e->q_off[B->q]; it.qb.len = B->read_len; it.qb.lp = lp_of(B->read_len, word); it.qb.rev = 0; }
+			if (B) { it.qb.off = (int32_t)e->q_off[B->q]; it.qb.len = B->read_len; it.qb.lp = lp_of(B->read_len, dual ? 1 : word); it.qb.rev = 0; }
 			it.ref_off = e->r_off[pt.r]; it.ref_len = ref_len; it.term_a = -1;
 			if (share && i > k && (pts[i].qa != pts[i - 1].qa || pts[i].qb != pts[i - 1].qb)) {
 				/* the queries change: fill the current CTA with dead items (empty range) of the previous queries */
@@ -1056,6 +1075,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 				memset(&d, 0, sizeof(d));
 				d.first_item = first_item; d.n_items = pl.n_chunks; d.half = h; d.ref_len = ref_len; d.read_len = X.read_len;
 				d.word = word; d.limit = limit; d.mask_len = X.mask_len; d.cm_off = (int64_t)cm_words; d.warm = pl.warm;
+				if (dual && h == 1) { d.word = 1; d.limit = S.limit_word; }
 				descs.push_back(d);
 				desc_aln.push_back(h ? pt.b : pt.a);
 			}
@@ -1067,7 +1087,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 		tr.lap("forward: fill (copy+kernel)");
 		e->timing.fill_forward_launches += 1;
 		e->timing.cells_forward += cells;
-		if (resolve_forward(e, descs, desc_aln, alns, word, S, word_first, refill, &cm_mode)) return -1;
+		if (resolve_forward(e, descs, desc_aln, alns, word, S, word_first, refill, &cm_mode, dual)) return -1;
 		tr.lap("forward: resolve");
 		k = k_end;
 	}
