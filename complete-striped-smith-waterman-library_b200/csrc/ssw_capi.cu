@@ -184,7 +184,8 @@ extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t 
 namespace {
 /* align the resident sequences and turn the records into heap s_align objects */
 int collect_batch(ssw_engine* e, const ssw_batch_params* params, int32_t n_queries, const int64_t* query_off,
-                  int32_t n_refs, const int64_t* ref_off, int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out)
+                  int32_t n_refs, const int64_t* ref_off, int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out,
+                  bool marked = false, int32_t* nm = nullptr)
 {
 	if (n_pairs < 0 || (n_pairs > 0 && (n_queries <= 0 || n_refs <= 0))) return -1;
 	std::vector<ssw_batch_result> res((size_t)n_pairs);
@@ -206,6 +207,23 @@ int collect_batch(ssw_engine* e, const ssw_batch_params* params, int32_t n_queri
 	int64_t used = 0;
 	const int rc = ssw_engine_align(e, params, n_pairs, pair_query, pair_ref, res.data(), pool.get(), cap + 8, &used);
 	if (rc) return rc;
+	if (marked) {
+		if (nm) for (int64_t p = 0; p < n_pairs; ++p) nm[p] = 0;
+		if (used > 0) {
+			/* a marked CIGAR has at most one word per aligned read base plus the deletions and two clips */
+			int64_t mcap = 0;
+			for (int64_t p = 0; p < n_pairs; ++p) if (res[p].cigar_len > 0) {
+				const int32_t q = pair_query ? pair_query[p] : (int32_t)(p / n_refs);
+				mcap += (query_off[q + 1] - query_off[q]) + res[p].cigar_len + 2;
+			}
+			std::unique_ptr<uint32_t[]> mpool(new uint32_t[(size_t)mcap + 8]);
+			int64_t mused = 0;
+			const int rc2 = ssw_engine_mark_mismatch(e, n_pairs, pair_query, pair_ref, res.data(), pool.get(), used, mpool.get(), mcap + 8, &mused, nm);
+			if (rc2) return rc2;
+			for (int64_t p = 0; p < n_pairs; ++p) out[p] = record_from(res[p], mpool.get());
+			return 0;
+		}
+	}
 	for (int64_t p = 0; p < n_pairs; ++p) out[p] = record_from(res[p], pool.get());
 	return 0;
 }
@@ -229,6 +247,27 @@ extern "C" int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
 		return collect_batch(e, params, n_queries, query_off, n_refs, ref_off, n_pairs, pair_query, pair_ref, out);
 	}
 	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_align_batch: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
+}
+
+extern "C" int ssw_align_batch_marked(ssw_engine* e, const ssw_batch_params* params,
+                                      int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                                      int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
+                                      int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                                      s_align** out, int32_t* nm)
+{
+	if (!params || !out) return -1;
+	try {
+		PoolGuard g(e ? nullptr : pool_acquire(nullptr, 0));
+		if (!e) e = g.e;
+		if (!e) return -1;
+		if (params->mask_len >= 0 && params->mask_len < 15)
+			fprintf(stderr, "When maskLen < 15, the function ssw_align doesn't return 2nd best alignment information.\n");
+		const int rc = ssw_engine_set_sequences(e, n_queries, queries, query_off, n_refs, refs, ref_off);
+		if (rc) return rc;
+		return collect_batch(e, params, n_queries, query_off, n_refs, ref_off, n_pairs, pair_query, pair_ref, out, true, nm);
+	}
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_align_batch_marked: %s\n", ex.what()); return -1; }
 	catch (...) { return -1; }
 }
 

@@ -83,6 +83,25 @@ void convert(const s_align& a, const int8_t* ref, const int8_t* query, int32_t q
 	out.mismatches = edits;
 }
 
+/* the same for a record whose CIGAR was already marked on the device (ssw_align_batch_marked): clips, '=' / 'X' runs and the
+ * mismatch count are there, only the text form is made here */
+void convert_marked(const s_align& a, int32_t nm, Alignment& out)
+{
+	out = Alignment();
+	out.sw_score = a.score1;
+	out.sw_score_next_best = a.score2;
+	out.ref_begin = a.ref_begin1;
+	out.ref_end = a.ref_end1;
+	out.query_begin = a.read_begin1;
+	out.query_end = a.read_end1;
+	out.ref_end_next_best = a.ref_end2;
+	CigarWriter w;
+	for (int32_t i = 0; i < a.cigarLen; ++i) w.put(cigar_int_to_len(a.cigar[i]), cigar_int_to_op(a.cigar[i]));
+	out.cigar.swap(w.words);
+	out.cigar_string.swap(w.text);
+	out.mismatches = nm;
+}
+
 }  // namespace
 
 void Aligner::DefaultTables()
@@ -204,12 +223,15 @@ bool Aligner::AlignBatch(const std::vector<std::string>& queries, const Filter& 
 	P.mask_len = maskLen < 0 ? -1 : std::max(maskLen, 15); P.score_size = 2;
 	const int64_t roff[2] = {0, (int64_t)ref_codes_.size()};
 	std::vector<s_align*> res(origin.size(), nullptr);
-	if (ssw_align_batch(nullptr, &P, (int32_t)origin.size(), codes.data(), off.data(), 1, ref_codes_.data(), roff,
-	                    (int64_t)origin.size(), nullptr, nullptr, res.data()))
+	std::vector<int32_t> nm(origin.size(), 0);
+	/* the '=' / 'X' expansion, the soft clips and the mismatch counts of every path come from the device (ssw_mark.cuh) */
+	if (ssw_align_batch_marked(nullptr, &P, (int32_t)origin.size(), codes.data(), off.data(), 1, ref_codes_.data(), roff,
+	                           (int64_t)origin.size(), nullptr, nullptr, res.data(), nm.data()))
 		return false;
 	for (size_t k = 0; k < origin.size(); ++k) {
 		if (!res[k]) { if (flags) (*flags)[origin[k]] = 1; continue; }
-		convert(*res[k], ref_codes_.data(), codes.data() + off[k], (int32_t)(off[k + 1] - off[k]), alignments[origin[k]]);
+		if (res[k]->cigarLen > 0) convert_marked(*res[k], nm[k], alignments[origin[k]]);
+		else convert(*res[k], ref_codes_.data(), codes.data() + off[k], (int32_t)(off[k + 1] - off[k]), alignments[origin[k]]);   /* no path: clips only */
 		if (flags) (*flags)[origin[k]] = res[k]->flag;
 		align_destroy(res[k]);
 	}

@@ -29,6 +29,7 @@
 #include "ssw_emul.cuh"
 #include "ssw_grid.cuh"
 #include "ssw_text.cuh"
+#include "ssw_mark.cuh"
 #include "../../include/ssw_batch.h"
 
 #include <chrono>
@@ -112,6 +113,7 @@ struct ssw_engine {
 
 	/* scratch */
 	SswDevBuf d_items, d_bests, d_alns, d_res, d_colmax, d_tb, d_bnd, d_park, d_emul, d_grid, d_out, d_sync;
+	SswDevBuf d_mark;                                        /* ssw_engine_mark_mismatch: tasks, input CIGARs, marked CIGARs */
 	SswDevBuf d_rf_items, d_rf_bests, d_rf_blk, d_rf_cm;     /* block-maximum mode: re-fill items, their (unused) bests, block ids, column maxima */
 	SswStagedD2H staged;
 	cudaStream_t side[3] = {nullptr, nullptr, nullptr};     /* traceback launches of different kernel shapes run side by side */
@@ -325,7 +327,7 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 {
 	if (!e) return;
 	cudaSetDevice(e->device);
-	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out, &e->d_sync, &e->d_rf_items, &e->d_rf_bests, &e->d_rf_blk, &e->d_rf_cm};
+	SswDevBuf* bufs[] = {&e->d_q, &e->d_r, &e->d_mat, &e->d_items, &e->d_bests, &e->d_alns, &e->d_res, &e->d_colmax, &e->d_tb, &e->d_bnd, &e->d_park, &e->d_emul, &e->d_grid, &e->d_out, &e->d_sync, &e->d_rf_items, &e->d_rf_bests, &e->d_rf_blk, &e->d_rf_cm, &e->d_mark};
 	for (SswDevBuf* b : bufs) b->release();
 	for (ssw_engine*& k : e->kids) if (k) { ssw_engine_destroy(k); k = nullptr; }
 	e->staged.release();
@@ -994,6 +996,7 @@ static int forward_pass(ssw_engine* e, const ssw_batch_params& P, std::vector<Al
 					 * latency-bound: shorter chunks, at the price of more warm-up columns (measured on config 2's re-fill
 					 * launch: 4.07 ms with the 16 x warm-up rule, 3.6 ms with 6 x) */
 					if (e->opt.chunk > 0) chunk = block ? (e->opt.chunk + SSW_CM_BLOCK - 1) / SSW_CM_BLOCK * SSW_CM_BLOCK : e->opt.chunk;
+					else if (latency) chunk = e->opt.small_chunk > 0 ? std::max<int64_t>(e->opt.small_chunk, 2 * warm) : std::max<int64_t>(1024, 2 * warm);   /* a lone call: the device is empty, its duration is one item's sweep */
 					else if (base_chunk < 4096) chunk = e->opt.small_chunk > 0 ? std::max<int64_t>(e->opt.small_chunk, 2 * warm) : std::max<int64_t>(2048, 6 * warm);
 					else chunk = std::max<int64_t>(std::max<int64_t>(4096, 16 * warm), auto_chunk);
 				}
@@ -1694,5 +1697,85 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
 	/* nothing may unwind through the C ABI (std::bad_alloc from the planners' vectors, std::length_error, ...) */
 	try { return engine_align_impl(e, params, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_cap, pool_used); }
 	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_align: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
+}
+
+/* mark_mismatch (ssw.c:1019-1074) for the CIGARs of a batch, on the device (ssw_mark.cuh) */
+static int mark_mismatch_impl(ssw_engine* e, int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                              ssw_batch_result* results, const uint32_t* cigar_pool, int64_t pool_used,
+                              uint32_t* out_pool, int64_t out_cap, int64_t* out_used, int32_t* nm)
+{
+	if (!e || n_pairs < 0 || (n_pairs && !results) || !out_used) return -1;
+	if ((pair_query == nullptr) != (pair_ref == nullptr)) return -1;
+	*out_used = 0;
+	if (n_pairs > 0 && (e->n_q <= 0 || e->n_r <= 0)) return -1;
+	SSW_CUDA_OK(cudaSetDevice(e->device));
+	std::vector<SswMarkTask> tasks;
+	std::vector<int64_t> owner;
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		if (nm) nm[p] = 0;
+		const ssw_batch_result& r = results[p];
+		if (r.status || r.cigar_off < 0 || r.cigar_len <= 0) continue;
+		const int32_t q = pair_query ? pair_query[p] : (int32_t)(p / e->n_r), rr = pair_ref ? pair_ref[p] : (int32_t)(p % e->n_r);
+		if (q < 0 || q >= e->n_q || rr < 0 || rr >= e->n_r || !cigar_pool || (int64_t)r.cigar_off + r.cigar_len > pool_used) return -1;
+		SswMarkTask t;
+		memset(&t, 0, sizeof(t));
+		t.ref_off = e->r_off[rr] + r.ref_begin1;
+		t.read_off = e->q_off[q];
+		t.cig_off = r.cigar_off; t.cig_len = r.cigar_len;
+		t.read_len = (int32_t)(e->q_off[q + 1] - e->q_off[q]); t.read_begin1 = r.read_begin1; t.read_end1 = r.read_end1;
+		tasks.push_back(t);
+		owner.push_back(p);
+	}
+	if (tasks.empty()) return 0;
+	const size_t o_in = (sizeof(SswMarkTask) * tasks.size() + 255) / 256 * 256;
+	const size_t in_bytes = ((size_t)pool_used * 4 + 255) / 256 * 256;
+	if (e->d_mark.ensure(o_in + in_bytes + 256)) return -1;
+	uint8_t* base = e->d_mark.as<uint8_t>();
+	SswMarkTask* d_tasks = reinterpret_cast<SswMarkTask*>(base);
+	uint32_t* d_in = reinterpret_cast<uint32_t*>(base + o_in);
+	SSW_CUDA_OK(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(SswMarkTask) * tasks.size(), cudaMemcpyHostToDevice, e->stream));
+	SSW_CUDA_OK(cudaMemcpyAsync(d_in, cigar_pool, (size_t)pool_used * 4, cudaMemcpyHostToDevice, e->stream));
+	const dim3 grid((unsigned)((tasks.size() + SSW_MARK_THREADS / 32 - 1) / (SSW_MARK_THREADS / 32)));
+	ssw_launch(ssw_mark_kernel<false>, grid, dim3(SSW_MARK_THREADS), 0, e->stream, d_tasks, (int)tasks.size(), (const int8_t*)e->d_q.as<int8_t>(),
+	           (const int8_t*)e->d_r.as<int8_t>(), (const uint32_t*)d_in, (uint32_t*)nullptr);
+	SSW_CUDA_OK(cudaGetLastError());
+	SSW_CUDA_OK(cudaMemcpyAsync(tasks.data(), d_tasks, sizeof(SswMarkTask) * tasks.size(), cudaMemcpyDeviceToHost, e->stream));
+	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	int64_t total = 0;
+	for (SswMarkTask& t : tasks) { t.out_off = total; total += t.out_len; }
+	if (total > out_cap || total > 0x7fffffff || !out_pool) { fprintf(stderr, "[libssw-b200] marked CIGAR pool too small (%lld words needed)\n", (long long)total); return -1; }
+	/* the output words go behind the input words */
+	const size_t o_out = o_in + in_bytes;
+	if (e->d_mark.cap < o_out + (size_t)total * 4 + 256) {
+		/* grow without losing the inputs: simplest is to re-stage them */
+		if (e->d_mark.ensure(o_out + (size_t)total * 4 + 256)) return -1;
+		base = e->d_mark.as<uint8_t>();
+		d_tasks = reinterpret_cast<SswMarkTask*>(base);
+		d_in = reinterpret_cast<uint32_t*>(base + o_in);
+		SSW_CUDA_OK(cudaMemcpyAsync(d_in, cigar_pool, (size_t)pool_used * 4, cudaMemcpyHostToDevice, e->stream));
+	}
+	uint32_t* d_out = reinterpret_cast<uint32_t*>(base + o_out);
+	SSW_CUDA_OK(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(SswMarkTask) * tasks.size(), cudaMemcpyHostToDevice, e->stream));
+	ssw_launch(ssw_mark_kernel<true>, grid, dim3(SSW_MARK_THREADS), 0, e->stream, d_tasks, (int)tasks.size(), (const int8_t*)e->d_q.as<int8_t>(),
+	           (const int8_t*)e->d_r.as<int8_t>(), (const uint32_t*)d_in, d_out);
+	SSW_CUDA_OK(cudaGetLastError());
+	SSW_CUDA_OK(cudaMemcpyAsync(out_pool, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost, e->stream));
+	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	for (size_t i = 0; i < tasks.size(); ++i) {
+		ssw_batch_result& r = results[owner[i]];
+		r.cigar_off = (int32_t)tasks[i].out_off; r.cigar_len = tasks[i].out_len;
+		if (nm) nm[owner[i]] = tasks[i].nm;
+	}
+	*out_used = total;
+	return 0;
+}
+
+extern "C" int ssw_engine_mark_mismatch(ssw_engine* e, int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                                        ssw_batch_result* results, const uint32_t* cigar_pool, int64_t pool_used,
+                                        uint32_t* out_pool, int64_t out_cap, int64_t* out_used, int32_t* nm)
+{
+	try { return mark_mismatch_impl(e, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_used, out_pool, out_cap, out_used, nm); }
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_mark_mismatch: %s\n", ex.what()); return -1; }
 	catch (...) { return -1; }
 }

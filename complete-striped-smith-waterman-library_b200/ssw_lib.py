@@ -220,6 +220,37 @@ class BatchAligner(object):
             raise RuntimeError("ssw_engine_align failed (%d)" % rv)
         return res, pool[: used.value]
 
+    def mark_mismatch(self, res, pool, pair_query=None, pair_ref=None):
+        """mark_mismatch (ssw.c:1019-1074) for every CIGAR of a batch, on the device (ssw_engine_mark_mismatch): `res` / `pool`
+        as returned by align() for the same pairs.  Returns (records with cigar_off / cigar_len pointing into the new pool,
+        marked pool, nm[int32])."""
+        f = self.lib.ssw_engine_mark_mismatch
+        f.argtypes = [ct.c_void_p, ct.c_int64, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), ct.c_void_p, ct.POINTER(ct.c_uint32),
+                      ct.c_int64, ct.POINTER(ct.c_uint32), ct.c_int64, ct.POINTER(ct.c_int64), ct.POINTER(ct.c_int32)]
+        f.restype = ct.c_int
+        out = np.array(res, dtype=RESULT_DTYPE, copy=True)
+        n_pairs = len(out)
+        if pair_query is None:
+            pq = pr = None
+            q_of = np.repeat(np.arange(self.n_q), self.n_r)
+        else:
+            pq_a = np.ascontiguousarray(pair_query, dtype=np.int32)
+            pr_a = np.ascontiguousarray(pair_ref, dtype=np.int32)
+            pq = pq_a.ctypes.data_as(ct.POINTER(ct.c_int32))
+            pr = pr_a.ctypes.data_as(ct.POINTER(ct.c_int32))
+            q_of = pq_a
+        has = out["cigar_len"] > 0
+        cap = int(np.sum(self._lens[0][q_of[has]] + out["cigar_len"][has] + 2)) + 8
+        pool_in = np.ascontiguousarray(pool, dtype=np.uint32)
+        marked = np.empty(cap, dtype=np.uint32)
+        nm = np.zeros(n_pairs, dtype=np.int32)
+        used = ct.c_int64(0)
+        rv = f(self.h, n_pairs, pq, pr, out.ctypes.data_as(ct.c_void_p), pool_in.ctypes.data_as(ct.POINTER(ct.c_uint32)), len(pool_in),
+               marked.ctypes.data_as(ct.POINTER(ct.c_uint32)), cap, ct.byref(used), nm.ctypes.data_as(ct.POINTER(ct.c_int32)))
+        if rv:
+            raise RuntimeError("ssw_engine_mark_mismatch failed (%d)" % rv)
+        return out, marked[: used.value], nm
+
     def timing(self):
         t = EngineTiming()
         self.lib.ssw_engine_last_timing(self.h, ct.byref(t))

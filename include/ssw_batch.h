@@ -90,6 +90,18 @@ int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
                      uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used);
 
 /*
+ * mark_mismatch (ssw.h:157-164; ssw.c:1019-1074) for the CIGARs of a whole batch, on the device: for every record of
+ * `results` that carries a CIGAR (words at cigar_pool[cigar_off ...]) the M runs are split into '=' and 'X' runs, soft
+ * clips are added for the unaligned ends of the read, and nm[p] (may be NULL) receives the number of mismatching +
+ * inserted + deleted bases.  The pairs must be those of the ssw_engine_align call that produced the records (same
+ * resident sequences, same pair lists).  On return cigar_off / cigar_len of those records point into out_pool;
+ * out_cap >= sum over the CIGAR-carrying pairs of (query length + 2) words is always enough.
+ */
+int ssw_engine_mark_mismatch(ssw_engine* e, int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                             ssw_batch_result* results, const uint32_t* cigar_pool, int64_t pool_used,
+                             uint32_t* out_pool, int64_t out_cap, int64_t* out_used, int32_t* nm);
+
+/*
  * Convenience: set_sequences + align + conversion to heap s_align records
  * (each to be released with align_destroy; NULL where ssw_align would return NULL).
  * e == NULL draws an engine from the pool that also serves ssw_align (engines are created on demand, up to
@@ -100,6 +112,14 @@ int ssw_align_batch(ssw_engine* e, const ssw_batch_params* params,
                     int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
                     int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
                     s_align** out);
+
+/* ssw_align_batch followed by ssw_engine_mark_mismatch: the CIGARs of the returned records already carry soft clips and
+ * '=' / 'X' runs (what mark_mismatch would make of them), nm[p] (may be NULL) the mismatch counts. */
+int ssw_align_batch_marked(ssw_engine* e, const ssw_batch_params* params,
+                           int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                           int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
+                           int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                           s_align** out, int32_t* nm);
 
 /* ssw_align_batch for text sequences (ssw_engine_set_sequences_text + align + s_align records); with
  * add_reverse_complement the queries n_queries .. 2*n_queries-1 are the reverse complements. */

@@ -72,6 +72,26 @@ int ssw_align_batch_text(ssw_engine* e, const ssw_batch_params* P, const int8_t*
 
 void align_destroy(s_align* a) { oracle_align_destroy((oracle_align_t*)a); }
 
+/* ssw_align_batch + the oracle's mark_mismatch per record (the product does this step on the device) */
+int ssw_align_batch_marked(ssw_engine* e, const ssw_batch_params* P,
+                           int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                           int32_t n_refs, const int8_t* refs, const int64_t* ref_off,
+                           int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out, int32_t* nm)
+{
+	const int rc = ssw_align_batch(e, P, n_queries, queries, query_off, n_refs, refs, ref_off, n_pairs, pair_query, pair_ref, out);
+	if (rc) return rc;
+	for (int64_t p = 0; p < n_pairs; ++p) {
+		if (nm) nm[p] = 0;
+		if (!out[p] || out[p]->cigarLen <= 0) continue;
+		const int32_t q = pair_query ? pair_query[p] : (int32_t)(p / n_refs);
+		const int32_t r = pair_ref ? pair_ref[p] : (int32_t)(p % n_refs);
+		const int32_t v = oracle_mark_mismatch(out[p]->ref_begin1, out[p]->read_begin1, out[p]->read_end1, refs + ref_off[r], queries + query_off[q],
+		                                       (int32_t)(query_off[q + 1] - query_off[q]), &out[p]->cigar, &out[p]->cigarLen);
+		if (nm) nm[p] = v;
+	}
+	return 0;
+}
+
 int32_t mark_mismatch(int32_t ref_begin1, int32_t read_begin1, int32_t read_end1, const int8_t* ref, const int8_t* read,
                       int32_t readLen, uint32_t** cigar, int32_t* cigarLen)
 {

@@ -525,3 +525,39 @@ def test_emulated_argument_validation(capfd):
     assert lib.ssw_engine_align(eng.h, ct.byref(P), 2, pq.ctypes.data_as(ct.POINTER(ct.c_int32)), pr.ctypes.data_as(ct.POINTER(ct.c_int32)),
                                 res.ctypes.data_as(ct.c_void_p), None, 0, ct.byref(used)) == -1
     eng.close()
+
+
+def test_emulated_device_mark_mismatch(oracle, capfd):
+    """ssw_engine_mark_mismatch (device) against the exported host mark_mismatch of the checker: soft clips, '=' / 'X' runs that
+    span several 32-column groups, insertions and deletions, NM; reads on both strands of the pair list, records without CIGAR."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    rng = np.random.default_rng(8)
+    mat = C.dna_matrix(2, 2)
+    refs = [rng.integers(0, 4, size=n).astype(np.int8) for n in (900, 400)]
+    reads = []
+    for k in range(10):
+        r = refs[k % 2]
+        core = C.mutate_read(rng, r, int(rng.integers(0, len(r) - 260)), int(rng.integers(40, 200)), 0.06, 0.03, 0.03)
+        reads.append(np.concatenate([rng.integers(0, 4, size=int(rng.integers(0, 9))).astype(np.int8), core,
+                                     rng.integers(0, 4, size=int(rng.integers(0, 9))).astype(np.int8)]))     # unaligned ends -> soft clips
+    reads.append(rng.integers(0, 4, size=30).astype(np.int8))
+    pq = np.array(list(range(len(reads))) * 2, dtype=np.int32)
+    pr = np.array([k % 2 for k in range(len(reads))] + [(k + 1) % 2 for k in range(len(reads))], dtype=np.int32)
+    eng.set_sequences(reads, refs)
+    res, pool = eng.align(mat, 5, 3, 1, flag=2, filters=30, filterd=32767, mask_len=20, score_size=2, pair_query=pq, pair_ref=pr)
+    assert int((res["cigar_len"] > 0).sum()) >= 8 and int((res["cigar_len"] == 0).sum()) >= 2     # filters: some pairs carry no path
+    out, marked, nm = eng.mark_mismatch(res, pool, pq, pr)
+    n_x = 0
+    for p in range(len(pq)):
+        q, r = reads[pq[p]], refs[pr[p]]
+        exp = oracle.align(q, r, mat, 5, 3, 1, 2, 30, 32767, 20, 2, mark=True)
+        if int(res[p]["cigar_len"]) == 0:
+            assert int(out[p]["cigar_len"]) == 0 and int(nm[p]) == 0
+            continue
+        got = [int(x) for x in marked[out[p]["cigar_off"]: out[p]["cigar_off"] + out[p]["cigar_len"]]]
+        assert got == exp["cigar_marked"] and int(nm[p]) == exp["nm"], (p, C.cigar_string(got), C.cigar_string(exp["cigar_marked"]))
+        n_x += sum(1 for w in got if (w & 15) == 8)
+    assert n_x > 5
+    eng.close()

@@ -472,6 +472,29 @@ def test_large_result_array_staged_copy(engine, checker, capfd):
         assert C.diff_results(got, exp) == [], p
 
 
+def test_device_mark_mismatch(engine, checker, capfd):
+    """ssw_engine_mark_mismatch: '=' / 'X' expansion, soft clips and NM of a batch on the device against the checker's own
+    mark_mismatch (ssw.c:1019-1074), for short reads with clipped ends and for 5 kbp reads (thousands of runs per CIGAR)."""
+    rng = np.random.default_rng(4242)
+    mat = C.dna_matrix(2, 2)
+    ref = rng.integers(0, 4, size=60_000).astype(np.int8)
+    reads = []
+    for k in range(40):
+        core = C.mutate_read(rng, ref, int(rng.integers(0, 59_000)), int(rng.integers(60, 240)), 0.06, 0.02, 0.02)
+        reads.append(np.concatenate([rng.integers(0, 4, size=int(rng.integers(0, 12))).astype(np.int8), core,
+                                     rng.integers(0, 4, size=int(rng.integers(0, 12))).astype(np.int8)]))
+    for k in range(8):
+        reads.append(C.mutate_read(rng, ref, int(rng.integers(0, 50_000)), 5000, 0.05, 0.02, 0.02))
+    engine.set_sequences(reads, [ref])
+    res, pool = engine.align(mat, 5, 3, 1, flag=2, filters=0, filterd=32767, mask_len=30, score_size=2)
+    out, marked, nm = engine.mark_mismatch(res, pool)
+    assert int((out["cigar_len"] > 0).sum()) == len(reads)
+    for i, q in enumerate(reads):
+        exp = checker.align(q, ref, mat, 5, 3, 1, 2, 0, 32767, 30, 2, mark=True)
+        got = [int(x) for x in marked[out[i]["cigar_off"]: out[i]["cigar_off"] + out[i]["cigar_len"]]]
+        assert got == exp["cigar_marked"] and int(nm[i]) == exp["nm"], i
+
+
 def test_two_engines_in_two_threads(capfd):
     """Independent engines (own stream, own scratch) used from two host threads at the same time give the results of a
     lone engine -- the way a caller drives several batches (or several GPUs) from one process."""

@@ -22,9 +22,11 @@ for name, rl, ql, flag in (("150bp_vs_1kbp_flag0", 1000, 150, 0), ("150bp_vs_1kb
     out[name] = round((time.perf_counter() - t0) / n * 1e6, 1)
 print({"us_per_call": out, "calls": n})
 if os.environ.get("SSW_TRACE"):
-    sys.stderr.write("---- one traced call (150 bp vs 1 kbp, flag 0) ----\n")
-    ref = rng.integers(0, 4, size=1000, dtype=np.int8)
-    q = C.mutate_read(rng, ref, 300, 150, 0.05, 0.01, 0.01)
-    t0 = time.perf_counter()
-    lib.align(q, ref, mat, 5, 3, 1, 0, 0, 32767, 75, 2)
-    sys.stderr.write("whole call %.1f us\n" % ((time.perf_counter() - t0) * 1e6))
+    for rl in (1000, 100_000):
+        sys.stderr.write("---- one traced call (150 bp vs %d bp, flag 0) ----\n" % rl)
+        ref = rng.integers(0, 4, size=rl, dtype=np.int8)
+        q = C.mutate_read(rng, ref, rl // 3, 150, 0.05, 0.01, 0.01)
+        lib.align(q, ref, mat, 5, 3, 1, 0, 0, 32767, 75, 2)
+        t0 = time.perf_counter()
+        lib.align(q, ref, mat, 5, 3, 1, 0, 0, 32767, 75, 2)
+        sys.stderr.write("whole call %.1f us\n" % ((time.perf_counter() - t0) * 1e6))
