@@ -474,6 +474,64 @@ extern "C" int ssw_engine_set_pair(ssw_engine* e, const int8_t* read, int32_t re
 	catch (...) { return -1; }
 }
 
+static int set_sequences_packed_impl(ssw_engine* e, int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                                     int32_t n_refs, const uint8_t* refs_packed, const int64_t* ref_off, int32_t bits, int32_t n)
+{
+	if (!e || (bits != 2 && bits != 4) || n < 1 || n > 64 || n_queries < 0 || n_refs < 0 || (n_queries && (!queries || !query_off)) ||
+	    (n_refs && (!refs_packed || !ref_off)))
+		return -1;
+	if (check_offsets("query", n_queries, query_off, SSW_MAX_QUERY_LETTERS, SSW_MAX_QUERY_LETTERS)) return -1;
+	if (check_offsets("reference", n_refs, ref_off, (int64_t)1 << 46, SSW_MAX_REF_LEN)) return -1;
+	SSW_CUDA_OK(cudaSetDevice(e->device));
+	e->cached_ref_len = -1;
+	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
+	e->n_q = n_queries; e->n_r = n_refs;
+	if (n_queries) e->q_off.assign(query_off, query_off + n_queries + 1); else e->q_off.assign(1, 0);
+	e->h_q.assign(queries, queries + qb);
+	e->h_r.clear(); e->h_r_off.clear();
+	e->r_len.resize(n_refs);
+	e->r_off.resize(n_refs);
+	int64_t total = 0;
+	for (int i = 0; i < n_refs; ++i) {
+		e->r_len[i] = (int32_t)(ref_off[i + 1] - ref_off[i]);
+		total += SSW_REF_PAD;
+		e->r_off[i] = total;
+		total += e->r_len[i];
+		total += SSW_REF_PAD;
+		total = (total + 15) / 16 * 16;
+	}
+	total += 2 * SSW_REF_PAD;
+	const size_t pk = (size_t)((rb * bits + 7) / 8);
+	const size_t o_ro = (pk + 255) / 256 * 256, o_rd = o_ro + 8 * (size_t)(n_refs + 1);
+	if (e->d_grid.ensure(o_rd + 8 * (size_t)(n_refs + 1) + 256)) return -1;
+	if (e->d_q.ensure((size_t)qb + 16)) return -1;
+	if (e->d_r.ensure((size_t)total)) return -1;
+	uint8_t* st = e->d_grid.as<uint8_t>();
+	if (qb) SSW_CUDA_OK(cudaMemcpyAsync(e->d_q.p, e->h_q.data(), (size_t)qb, cudaMemcpyHostToDevice, e->stream));
+	SSW_CUDA_OK(cudaMemsetAsync(e->d_r.p, n, (size_t)total, e->stream));          /* null letters everywhere, codes on top */
+	if (n_refs && rb) {
+		SSW_CUDA_OK(cudaMemcpyAsync(st, refs_packed, pk, cudaMemcpyHostToDevice, e->stream));
+		SSW_CUDA_OK(cudaMemcpyAsync(st + o_ro, ref_off, 8 * (size_t)(n_refs + 1), cudaMemcpyHostToDevice, e->stream));
+		SSW_CUDA_OK(cudaMemcpyAsync(st + o_rd, e->r_off.data(), 8 * (size_t)n_refs, cudaMemcpyHostToDevice, e->stream));
+		const unsigned blocks = (unsigned)std::min<int64_t>((rb + 255) / 256, (int64_t)e->sm_count * 16);
+		ssw_launch(ssw_unpack_kernel, dim3(blocks), dim3(256), 0, e->stream, rb, n_refs, bits, (const uint8_t*)st,
+		           (const int64_t*)reinterpret_cast<int64_t*>(st + o_ro), (const int64_t*)reinterpret_cast<int64_t*>(st + o_rd), e->d_r.as<int8_t>());
+		SSW_CUDA_OK(cudaGetLastError());
+	}
+	SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+	e->padded_n = n;
+	e->from_text = true;        /* no unpacked host copy to re-pad from: the alphabet size is fixed by this call */
+	return 0;
+}
+
+extern "C" int ssw_engine_set_sequences_packed(ssw_engine* e, int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                                               int32_t n_refs, const uint8_t* refs_packed, const int64_t* ref_off, int32_t bits, int32_t n)
+{
+	try { return set_sequences_packed_impl(e, n_queries, queries, query_off, n_refs, refs_packed, ref_off, bits, n); }
+	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_set_sequences_packed: %s\n", ex.what()); return -1; }
+	catch (...) { return -1; }
+}
+
 static int set_sequences_text_impl(ssw_engine* e,
                                    int32_t n_queries, const char* queries, const int64_t* query_off,
                                    int32_t n_refs, const char* refs, const int64_t* ref_off,

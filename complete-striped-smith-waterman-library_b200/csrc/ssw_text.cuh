@@ -66,4 +66,23 @@ ssw_translate_kernel(SswTextArgs A, const uint8_t* __restrict__ q_text, const in
 	}
 }
 
+/* References delivered as packed codes (the CLI's nucleotide codes are 0..4, main.c:84-93, i.e. 4 bits, or 2 bits
+ * for N-free sequences): `packed` is the bit stream of the concatenated references, base i at bits [i*bits, i*bits + bits)
+ * (low bits first), unpacked here into the engine's padded 1-byte layout.  The resident layout stays one byte per base on
+ * purpose: the fill kernel is bound by the ALU pipe and a per-step nibble extract costs ALU slots (profiles/dpx_peak_r2.json:
+ * letter_fetch); the packing halves / quarters what crosses PCIe and what the caller keeps in host memory. */
+__global__ void __launch_bounds__(256)
+ssw_unpack_kernel(int64_t r_bases, int32_t n_r, int32_t bits, const uint8_t* __restrict__ packed, const int64_t* __restrict__ r_off,
+                  const int64_t* __restrict__ r_dst, int8_t* __restrict__ r_codes)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	const unsigned mask = (1u << bits) - 1u;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r_bases; i += stride) {
+		int lo = 0, hi = n_r;
+		while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (r_off[mid] <= i) lo = mid; else hi = mid; }
+		const int64_t bit = i * bits;
+		r_codes[r_dst[lo] + (i - r_off[lo])] = (int8_t)((packed[bit >> 3] >> (bit & 7)) & mask);
+	}
+}
+
 #endif /* SSW_TEXT_CUH */

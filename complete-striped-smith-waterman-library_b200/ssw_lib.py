@@ -184,6 +184,30 @@ class BatchAligner(object):
         self.n_q, self.n_r = len(ql), len(rs)
         self._lens = (ql, np.diff(ro))
 
+    def set_sequences_packed(self, queries, refs, bits, n):
+        """References delivered as a packed bit stream (bits = 2 or 4 per base, low bits first; unpacked on the device by
+        ssw_engine_set_sequences_packed); queries as plain codes.  `n` = alphabet size of the later align() calls."""
+        qc, qo = concat(queries)
+        rc, ro = concat(refs)
+        assert bits in (2, 4) and (rc.size == 0 or int(rc.max()) < (1 << bits))
+        per = 8 // bits
+        padded = np.zeros((len(rc) + per - 1) // per * per, dtype=np.uint8)
+        padded[: len(rc)] = rc.astype(np.uint8)
+        packed = np.zeros(len(padded) // per, dtype=np.uint8)
+        for k in range(per):
+            packed |= (padded[k::per] << (bits * k)).astype(np.uint8)
+        f = self.lib.ssw_engine_set_sequences_packed
+        f.argtypes = [ct.c_void_p, ct.c_int32, ct.POINTER(ct.c_int8), ct.POINTER(ct.c_int64), ct.c_int32, ct.POINTER(ct.c_uint8),
+                      ct.POINTER(ct.c_int64), ct.c_int32, ct.c_int32]
+        f.restype = ct.c_int
+        rv = f(self.h, len(queries), qc.ctypes.data_as(ct.POINTER(ct.c_int8)), qo.ctypes.data_as(ct.POINTER(ct.c_int64)), len(refs),
+               packed.ctypes.data_as(ct.POINTER(ct.c_uint8)), ro.ctypes.data_as(ct.POINTER(ct.c_int64)), int(bits), int(n))
+        if rv:
+            raise RuntimeError("ssw_engine_set_sequences_packed failed (%d)" % rv)
+        self.n_q, self.n_r = len(queries), len(refs)
+        self._lens = (np.diff(qo), np.diff(ro))
+        return len(packed)
+
     def align(self, mat, n, gap_open=3, gap_extend=1, flag=0, filters=0, filterd=0, mask_len=-1, score_size=2,
               pair_query=None, pair_ref=None, want_cigar=None, out=None):
         """Align pairs of the resident sequences; returns (results[RESULT_DTYPE], cigar_pool[uint32]).

@@ -78,6 +78,17 @@ int ssw_engine_set_sequences_text(ssw_engine* e,
                                   const int8_t* table, int32_t n, int32_t add_reverse_complement);
 
 /*
+ * The same with the references delivered PACKED: `refs_packed` is the bit stream of the concatenated reference codes, base i at
+ * bits [i*bits, i*bits + bits) (low bits first), bits = 4 (the CLI's nucleotide codes 0..4, main.c:84-93) or 2 (N-free
+ * sequences); ref_off are offsets in BASES.  The stream is unpacked on the device; `n` is the alphabet size of the later
+ * align calls.  Queries are plain codes.
+ */
+int ssw_engine_set_sequences_packed(ssw_engine* e,
+                                    int32_t n_queries, const int8_t* queries, const int64_t* query_off,
+                                    int32_t n_refs, const uint8_t* refs_packed, const int64_t* ref_off,
+                                    int32_t bits, int32_t n);
+
+/*
  * Align pairs of resident sequences.
  *   pair_query / pair_ref   n_pairs indices; both NULL: the full grid, pair p = query p / n_refs x ref p % n_refs
  *   results                 n_pairs records (host memory)

@@ -561,3 +561,25 @@ def test_emulated_device_mark_mismatch(oracle, capfd):
         n_x += sum(1 for w in got if (w & 15) == 8)
     assert n_x > 5
     eng.close()
+
+
+def test_emulated_packed_references(capfd):
+    """References delivered as a 4-bit (codes 0..4 incl. N) or 2-bit (N-free) packed stream, unpacked on the device, give the
+    results of the plain one-byte-per-base input: several references of odd lengths (bases straddling bytes), CIGARs."""
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    L = _pkg()
+    eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+    rng = np.random.default_rng(12)
+    mat = C.dna_matrix(2, 2)
+    for bits, top in ((4, 5), (2, 4)):
+        refs = [rng.integers(0, top, size=n).astype(np.int8) for n in (301, 77, 1, 514)]
+        reads = [C.mutate_read(rng, refs[k % 4] if len(refs[k % 4]) > 60 else refs[0], 3, 50, 0.05, 0.02, 0.02) for k in range(6)]
+        pq = np.repeat(np.arange(6), 4)
+        pr = np.tile(np.arange(4), 6)
+        eng.set_sequences(reads, refs)
+        want, want_pool = eng.align(mat, 5, 3, 1, flag=2, filters=0, filterd=32767, mask_len=25, score_size=2, pair_query=pq, pair_ref=pr)
+        nbytes = eng.set_sequences_packed(reads, refs, bits, 5)
+        assert nbytes == (sum(len(r) for r in refs) * bits + 7) // 8
+        got, got_pool = eng.align(mat, 5, 3, 1, flag=2, filters=0, filterd=32767, mask_len=25, score_size=2, pair_query=pq, pair_ref=pr)
+        assert C.compare_records(got, got_pool, want, want_pool) == [] and int((want["cigar_len"] > 0).sum()) >= 6
+    eng.close()

@@ -495,6 +495,20 @@ def test_device_mark_mismatch(engine, checker, capfd):
         assert got == exp["cigar_marked"] and int(nm[i]) == exp["nm"], i
 
 
+def test_packed_reference_input(engine, capfd):
+    """A 3 Mbp reference delivered as a 4-bit and as a 2-bit packed stream (unpacked on the device) gives the records of the
+    plain one-byte-per-base input, block column maxima and all."""
+    ref, reads = C.make_dna_workload(3_000_000, 96, 150, seed_ref=77, seed_reads=78)
+    mat = C.dna_matrix(2, 2)
+    engine.set_sequences(reads, [ref])
+    want, want_pool = engine.align(mat, 5, 3, 1, flag=0, mask_len=75, score_size=2)
+    for bits in (4, 2):
+        nbytes = engine.set_sequences_packed(reads, [ref], bits, 5)
+        assert nbytes == len(ref) * bits // 8
+        got, got_pool = engine.align(mat, 5, 3, 1, flag=0, mask_len=75, score_size=2)
+        assert C.compare_records(got, got_pool, want, want_pool) == []
+
+
 def test_two_engines_in_two_threads(capfd):
     """Independent engines (own stream, own scratch) used from two host threads at the same time give the results of a
     lone engine -- the way a caller drives several batches (or several GPUs) from one process."""
