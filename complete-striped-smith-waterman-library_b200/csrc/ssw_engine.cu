@@ -66,7 +66,8 @@ struct SswOptions {
 	int grid_min_pairs = 32768;     /* "grid_min": smaller grids use the general path */
 	int64_t grid_split_pairs = (int64_t)4 << 20;   /* "grid_split": grids of at least this many pairs are cut into launch groups whose records are copied back while the next group computes */
 	int grid_group_qp = 16;         /* "grid_group": smallest such group, in query pairs */
-	int64_t latency_cols = 1 << 20; /* "latency_cols": passes over at most this many reference columns use the 32-lane instances */
+	int64_t latency_cols = (int64_t)5 << 19;   /* "latency_cols": passes over at most this many reference columns (2.6 M: one wave of
+	                                            * 1,024-column items on 148 SMs) use the 32-lane instances */
 	int force_inst = -1;            /* "inst" (measurements): use this forward instance whenever it covers the query */
 	int tb_maxbw = SSW_TBP_MAXBW;   /* "tb_maxbw": widest band handled by the shared-memory traceback kernel */
 	int tb_spec = -1;               /* "tb_spec": 1 = band-doubling rounds of a task side by side (speculative kernel), 0 = one after the other, -1 = automatic (small batches) */
@@ -346,7 +347,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!e) return ssw_default_engines_option(name, value);
 	SswOptions& o = e->opt;
 	if (!strcmp(name, "slices")) { o.slices = value >= 1 && value <= 3 ? (int)value : 0; return 0; }
-	if (!strcmp(name, "latency_cols")) { o.latency_cols = value < 0 ? 0 : value; return 0; }
+	if (!strcmp(name, "latency_cols")) { o.latency_cols = value < 0 ? ((int64_t)5 << 19) : value; return 0; }
 	if (!strcmp(name, "parts")) { o.strip_parts = value == 1 || value == 2 || value == 4 ? (int)value : 0; return 0; }
 	if (!strcmp(name, "small_chunk")) { o.small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
 	if (!strcmp(name, "chunk")) { o.chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
