@@ -64,7 +64,7 @@ def test_emulated_random_vs_oracle(emu, oracle, latency, capfd):
     rng = np.random.default_rng(424242 + int(latency))
     bad = []
     n = 0
-    while n < 110:
+    while n < 80:
         c = random_case(rng)           # every gap regime, incl. gapO <= gapE (lane-literal kernel)
         n += 1
         d = C.diff_results(emu.align(**c), oracle.align(**c))
@@ -130,19 +130,17 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
     ref2 = np.concatenate([rng.integers(0, 4, size=700).astype(np.int8), ref[900:1500], rng.integers(0, 4, size=150).astype(np.int8)])
     refs2 = [ref, ref2, ref[:900].copy()]
     eng.set_sequences(reads, refs2)
-    for flag in (2,):
-        res, pool = eng.align(mat, 5, 3, 1, flag=flag, filterd=32767, mask_len=100, score_size=2)
-        k = 0
-        for q in reads:
-            for rr in refs2:
-                exp = oracle.align(q, rr, mat, 5, 3, 1, flag, 0, 32767, 100, 2)
-                r = res[k]
-                got = {f: int(r[f]) for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
-                got["cigar"] = [int(x) for x in pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
-                assert C.diff_results(got, exp) == [], (flag, k)
-                k += 1
     # the same batch cut into slices that run on helper engines (views of the resident sequences, own scratch)
     base_res, base_pool = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=100, score_size=2)
+    k = 0
+    for q in reads:
+        for rr in refs2:
+            exp = oracle.align(q, rr, mat, 5, 3, 1, 0x0f, 0, 32767, 100, 2)
+            r = base_res[k]
+            got = {f: int(r[f]) for f in ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "flag")}
+            got["cigar"] = [int(x) for x in base_pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
+            assert C.diff_results(got, exp) == [], k
+            k += 1
     for slices in (3,):
         eng.set_option("slices", slices)
         res, pool = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=100, score_size=2)
