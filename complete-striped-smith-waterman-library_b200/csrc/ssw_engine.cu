@@ -320,7 +320,6 @@ extern "C" ssw_engine* ssw_engine_create(int device)
 	e->sm_count = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return nullptr; }
 	memset(&e->timing, 0, sizeof(e->timing));
-	++ssw_live_engines();
 	return e;
 }
 
@@ -335,7 +334,6 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 	for (cudaStream_t& st : e->side) if (st) { cudaStreamDestroy(st); st = nullptr; }
 	for (cudaEvent_t ev : e->grid_events) if (ev) cudaEventDestroy(ev);
 	if (e->stream) cudaStreamDestroy(e->stream);
-	--ssw_live_engines();
 	delete e;
 }
 
@@ -1754,7 +1752,7 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
                                 uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
 {
 	/* nothing may unwind through the C ABI (std::bad_alloc from the planners' vectors, std::length_error, ...) */
-	try { return engine_align_impl(e, params, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_cap, pool_used); }
+	try { SswBusyGuard busy; return engine_align_impl(e, params, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_cap, pool_used); }
 	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_align: %s\n", ex.what()); return -1; }
 	catch (...) { return -1; }
 }

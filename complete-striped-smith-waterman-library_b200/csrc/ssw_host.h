@@ -16,10 +16,11 @@
  * this changed (cudaMemGetInfo costs milliseconds while a monitoring tool polls the driver) */
 inline std::atomic<unsigned long long>& ssw_alloc_epoch() { static std::atomic<unsigned long long> n{1}; return n; }
 
-/* engines alive in this process: every planner may claim 1 / (engines + 1) of the free device memory for its scratch, so
- * that several engines on one device (helper engines of a sliced batch, the pool behind ssw_align, user-made ones) cannot
- * claim the same half twice */
+/* engines currently inside an align call: every planner may claim 1 / (engines + 1) of the free device memory for its
+ * scratch, so that several engines working on one device at the same time (helper engines of a sliced batch, concurrent
+ * ssw_align callers, user-made engines in several threads) cannot claim the same half twice; idle engines do not count */
 inline std::atomic<int>& ssw_live_engines() { static std::atomic<int> n{0}; return n; }
+struct SswBusyGuard { SswBusyGuard() { ++ssw_live_engines(); } ~SswBusyGuard() { --ssw_live_engines(); } };
 inline size_t ssw_budget_share(size_t bytes) { const int n = ssw_live_engines().load(); return bytes / (size_t)((n < 1 ? 1 : n) + 1); }
 
 /* 64-bit content hash (four interleaved multiply-xor lanes over 8-byte words): the resident-reference cache of ssw_align */

@@ -620,7 +620,7 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 		t.max = 0; t.max_i = 0; t.max_j = 0; t.status = SSW_TB_WIDER; t.cig_len = 0;
 	}
 	const size_t free_b = ssw_free_device_bytes();
-	const size_t budget = std::max<size_t>((size_t)64 << 20, (free_b + scratch->cap) / 2);
+	const size_t budget = std::max<size_t>((size_t)64 << 20, ssw_budget_share(free_b + scratch->cap));
 	/* Rounds of band doubling run side by side by the speculative kernel (1: not used).  Narrow bands (up to four tiles per row)
 	 * cost one tile latency per row whatever their width, so all of them go together; of wider ones at most two, so that
 	 * a task that needs only the first loses little. */
