@@ -63,6 +63,7 @@ static inline void ssw_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 #define SSW_REF_PAD 64          /* null letters stored before and after every reference */
 #define SSW_NEG16 (-32768)      /* score of dead rows / null letters: keeps H at exactly 0 */
 #define SSW_CM_NONE ((int64_t)(-0x7fffffffffffffffLL - 1))   /* cm_off value: no column maxima are recorded */
+#define SSW_ROW_UNARMED 0x3ffffffe  /* best-cell row of an item whose maximum lies before its armed range: the pair is re-done with arm 0 */
 #define SSW_CM_BLOCK 64         /* columns per block of the block-maximum mode (CM == 2) of the fill kernel */
 
 /* ---- packed s16x2 helpers --------------------------------------------------- */
@@ -92,7 +93,8 @@ struct SswItem {
 	SswQuery qa, qb;    /* qb.len == 0: half B is dead */
 	int64_t ref_off;    /* offset of reference column 0 inside the padded reference array */
 	int32_t ref_len;
-	int32_t cend;       /* reverse pass: column of scan index 0 (= ref_end1); forward: unused */
+	int32_t cend;       /* reverse pass: column of scan index 0 (= ref_end1); forward pass: `arm`, the first scan position whose
+	                     * best cell gets its row recorded (0: all of them; see SSW_ROW_UNARMED) */
 	int32_t p0, p1;     /* counted scan range */
 	int32_t warm;       /* warm-up scan positions before p0 (state build-up, results discarded) */
 	int32_t term_a;     /* reverse pass: stop once a column maximum equals this (score1); else -1 */
@@ -130,7 +132,7 @@ struct SswFillResult {
 	int32_t read;       /* end_read  */
 	int32_t score2;
 	int32_t ref2;
-	int32_t overflow;   /* 1: byte overflow, 2: 16-bit head-room exhausted */
+	int32_t overflow;   /* 1: byte overflow, 2: 16-bit head-room exhausted, 3: best cell before the armed range (row unknown: re-do) */
 	int32_t pad_[2];
 };
 

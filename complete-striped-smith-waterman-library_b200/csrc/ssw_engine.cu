@@ -66,6 +66,9 @@ struct SswOptions {
 	int grid_min_pairs = 32768;     /* "grid_min": smaller grids use the general path */
 	int64_t grid_split_pairs = (int64_t)4 << 20;   /* "grid_split": grids of at least this many pairs are cut into launch groups whose records are copied back while the next group computes */
 	int grid_group_qp = 16;         /* "grid_group": smallest such group, in query pairs */
+	int grid_arm = -1;              /* "grid_arm": best-cell rows of the device-planned grid are recorded in the last k columns of a reference only
+	                                 * (pairs whose maximum lies earlier are re-done): -1 automatic (protein-like alphabets: padded query
+	                                 * length / 2 + 64, switched off when a pilot group re-does more than 2 % of its pairs), 0 off, k > 0 fixed */
 	int64_t latency_cols = (int64_t)5 << 19;   /* "latency_cols": passes over at most this many reference columns (2.6 M: one wave of
 	                                            * 1,024-column items on 148 SMs) use the 32-lane instances */
 	int force_inst = -1;            /* "inst" (measurements): use this forward instance whenever it covers the query */
@@ -108,6 +111,7 @@ struct ssw_engine {
 	std::vector<int64_t> h_r_off;
 	int padded_n = -1;               /* null letter currently stored in the reference pads */
 	bool from_text = false;          /* sequences were translated on the device: no host copy to re-pad from */
+	bool grid_arm_ok = true;         /* late arming paid off for the resident sequences so far (reset by set_sequences*) */
 	int64_t cached_ref_len = -1;     /* ssw_engine_set_pair: length and content hash of the single resident reference (-1: none) */
 	uint64_t cached_ref_hash = 0;
 	SswDevBuf d_q, d_r, d_mat;
@@ -352,6 +356,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!strcmp(name, "cm_block")) { o.cm_block = value < 0 ? -1 : (value ? 1 : 0); return 0; }
 	if (!strcmp(name, "cm_budget_mb")) { o.cm_budget = value <= 0 ? 0 : value << 20; return 0; }
 	if (!strcmp(name, "grid_split")) { o.grid_split_pairs = value < 0 ? (int64_t)4 << 20 : value; return 0; }
+	if (!strcmp(name, "grid_arm")) { o.grid_arm = value < 0 ? -1 : (int)value; return 0; }
 	if (!strcmp(name, "grid_group")) { o.grid_group_qp = value < 1 ? 16 : (int)value; return 0; }
 	if (!strcmp(name, "grid_min")) { o.grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
 	if (!strcmp(name, "inst")) { o.force_inst = (int)value; return 0; }       /* index into kInst */
@@ -423,6 +428,7 @@ static int set_sequences_impl(ssw_engine* e,
 	e->n_q = n_queries; e->n_r = n_refs;
 	e->from_text = false;
 	e->cached_ref_len = -1;
+	e->grid_arm_ok = true;
 	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
 	if (n_queries) e->q_off.assign(query_off, query_off + n_queries + 1); else e->q_off.assign(1, 0);
 	e->h_q.assign(queries, queries + qb);
@@ -483,6 +489,7 @@ static int set_sequences_packed_impl(ssw_engine* e, int32_t n_queries, const int
 	if (check_offsets("reference", n_refs, ref_off, (int64_t)1 << 46, SSW_MAX_REF_LEN)) return -1;
 	SSW_CUDA_OK(cudaSetDevice(e->device));
 	e->cached_ref_len = -1;
+	e->grid_arm_ok = true;
 	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
 	e->n_q = n_queries; e->n_r = n_refs;
 	if (n_queries) e->q_off.assign(query_off, query_off + n_queries + 1); else e->q_off.assign(1, 0);
@@ -557,6 +564,7 @@ static int set_sequences_text_impl(ssw_engine* e,
 	if (check_offsets("reference", n_refs, ref_off, (int64_t)1 << 46, SSW_MAX_REF_LEN)) return -1;
 	SSW_CUDA_OK(cudaSetDevice(e->device));
 	e->cached_ref_len = -1;
+	e->grid_arm_ok = true;
 	const int64_t qb = n_queries ? query_off[n_queries] : 0, rb = n_refs ? ref_off[n_refs] : 0;
 	e->n_q = n_queries * (1 + rc); e->n_r = n_refs;
 	if (n_queries) e->q_off.assign(query_off, query_off + n_queries + 1); else e->q_off.assign(1, 0);
@@ -1356,6 +1364,13 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 	tr.lap("grid: tables");
 	struct GridGroup { cudaEvent_t ev; int32_t q_lo, q_n; bool contiguous; };
 	std::vector<GridGroup> groups;
+	/* Late arming of the best-cell bookkeeping (ssw_fill.cuh): rows are recorded in the last arm_tail columns of every
+	 * reference only.  Automatic for protein-like alphabets, where the running maximum grows with every column and the
+	 * maximum of a pair lies near the end of the reference; a small pilot group goes first and the rest of the grid is
+	 * armed from column 0 again if more than 2 % of the pilot's pairs had to be re-done. */
+	bool arm_on = e->opt.grid_arm > 0 || (e->opt.grid_arm < 0 && P.n > 8 && e->grid_arm_ok);
+	bool pilot_pending = arm_on && e->opt.grid_arm < 0;
+	int64_t pilot_pairs = 0;
 	size_t k = 0;
 	while (k < order.size()) {
 		const int inst = q_inst[order[k]];
@@ -1368,6 +1383,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		 * copied to the host while the next group computes (115 MB of records per million pairs) */
 		if ((int64_t)n_q * n_r >= e->opt.grid_split_pairs)
 			max_qp = std::min<size_t>(max_qp, std::max<size_t>((size_t)std::max(e->opt.grid_group_qp, 1), ((size_t)n_q / 2 + 7) / 8));
+		if (pilot_pending && (size_t)n_q / 2 >= 16) max_qp = std::min<size_t>(max_qp, std::max<size_t>(2, (size_t)n_q / 64));   /* the pilot: 1/32 of the queries */
 		std::vector<int2> qps;
 		const size_t k_first = k;
 		while (k < order.size() && q_inst[order[k]] == inst && qps.size() < max_qp) {
@@ -1377,7 +1393,13 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 			qps.push_back(pr);
 		}
 		SswGridArgs A;
-		A.n_qp = (int32_t)qps.size(); A.n_r = n_r; A.n_r_pad = n_r_pad; A.word = word; A.limit = limit; A.pad_ = 0; A.cm_words_per_qp = cm_per_qp;
+		A.n_qp = (int32_t)qps.size(); A.n_r = n_r; A.n_r_pad = n_r_pad; A.word = word; A.limit = limit; A.cm_words_per_qp = cm_per_qp;
+		A.arm_tail = 0;
+		if (arm_on) {
+			int lp_max = 0;
+			for (const int2& pr : qps) { lp_max = std::max(lp_max, qt[pr.x].lp); if (pr.y >= 0) lp_max = std::max(lp_max, qt[pr.y].lp); }
+			A.arm_tail = e->opt.grid_arm > 0 ? e->opt.grid_arm : lp_max / 2 + 64;
+		}
 		const int64_t n_items = (int64_t)A.n_qp * n_r_pad, n_desc = (int64_t)A.n_qp * n_r * 2;
 		if (n_items > 0x7fffffff || n_desc > 0x7fffffff) return 0;
 		if (e->d_items.ensure(sizeof(SswItem) * (size_t)n_items)) return -1;
@@ -1426,6 +1448,15 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		gg.q_lo = order[k_first]; gg.q_n = (int32_t)(k - k_first); gg.contiguous = true;
 		for (size_t i = k_first; i < k; ++i) if (order[i] != gg.q_lo + (int32_t)(i - k_first)) gg.contiguous = false;
 		groups.push_back(gg);
+		if (pilot_pending) {
+			/* how many of the pilot's pairs must be re-done?  (byte overflows count too: either way the grid path does not pay off) */
+			pilot_pending = false;
+			int32_t n_now = 0;
+			SSW_CUDA_OK(cudaMemcpyAsync(&n_now, gb + o_cnt, 4, cudaMemcpyDeviceToHost, e->stream));
+			SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
+			pilot_pairs = (int64_t)A.n_qp * 2 * n_r;
+			if ((int64_t)n_now * 50 > pilot_pairs) { arm_on = false; e->grid_arm_ok = false; }
+		}
 		tr.lap("grid: launch group");
 	}
 	/* every launch is queued; bring the records back group by group on the copy stream while later groups still compute */
@@ -1520,6 +1551,8 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 		rc = emul_pass(e, P, alns, sat, 1, 0, S);
 		if (rc) return rc;
 	}
+	for (int64_t p = 0; p < n_pairs; ++p)
+		if (alns[p].fwd.overflow == 3) { fprintf(stderr, "[libssw-b200] internal: unarmed best cell outside the grid path\n"); return -1; }
 	std::vector<uint8_t> null_result((size_t)n_pairs, 0);
 	for (int64_t p = 0; p < n_pairs; ++p) {
 		const Aln& a = alns[p];

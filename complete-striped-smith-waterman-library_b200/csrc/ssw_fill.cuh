@@ -265,6 +265,13 @@ __device__ static __forceinline__ void ssw_track(SswLaneBest& lb, SswSnap<R, SME
 	}
 }
 
+/* a lane whose best was never recorded by an event (position -1) has no row to offer */
+__device__ static __forceinline__ void ssw_track_unrecorded(SswLaneBest& lb)
+{
+	if (lb.pos0 < 0) lb.row0 = SSW_ROW_UNARMED;
+	if (lb.pos1 < 0) lb.row1 = SSW_ROW_UNARMED;
+}
+
 /* after the sweep: smallest row of this lane that held the lane's best value when it was recorded */
 template <int R>
 __device__ static __forceinline__ void ssw_track_rows(SswLaneBest& lb, const SswSnap<R, true>& sn, int row_base)
@@ -403,7 +410,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	for (int k = 0; k < R; ++k) { Hd[k] = 0; E[k] = 0; }
 	uint32_t outH = 0, outF = 0, outC = 0;
 	SswLaneBest lb;
-	lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
+	lb.best = 0; lb.pos0 = lb.pos1 = -1; lb.row0 = lb.row1 = 0;      /* position -1: no recorded event (yet) */
 	SswSnap<R> snap;
 	ssw_snap_init<R>(snap, reinterpret_cast<uint4*>(smem + (size_t)(share ? 1 : nwarps) * (size_t)(n + 1) * 32 * R), (int)threadIdx.x);
 	uint32_t blk_acc = 0;                               /* CM == 2: running maximum of the current block (last lane) */
@@ -417,6 +424,11 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 			lb.best = __vmaxs2(lb.best, __vadd2(floor2, 0xffffffffu));
 		}
 		const bool maybe_counted = sp0 + U - 1 >= it.p0 && sp0 < it.p1;   /* this body touches the counted range */
+		/* Late arming (DIR > 0, items without warm-up): before scan position `arm` only the VALUE of the running best is kept --
+		 * no position, no snapshot, no branch.  If the item's maximum turns out to lie there (its position stays -1) the
+		 * resolve step flags the pair and it is re-done with arm 0.  Protein grids: the running maximum grows on every
+		 * column, the best cell lies in the last third of the reference for 99.99 % of the pairs. */
+		const bool unarmed = DIR > 0 && sp0 + U - 1 < it.cend;
 #pragma unroll
 		for (int j = 0; j < U; ++j) {
 			/* values crossing the lane boundary */
@@ -435,7 +447,11 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 
 			/* running best of this lane's rows (strict increase only; rare path) */
 			const uint32_t nb = __vmaxs2(lb.best, own);
-			if (nb != lb.best && maybe_counted) ssw_track<R>(lb, snap, nb, Hn, sp0 + j, it.p0, it.p1);
+			if (unarmed) lb.best = nb;
+			else if (nb != lb.best && maybe_counted) {
+				if (DIR > 0 && sp0 + j < it.cend) lb.best = nb;          /* the body that crosses `arm`: still before it */
+				else ssw_track<R>(lb, snap, nb, Hn, sp0 + j, it.p0, it.p1);
+			}
 		}
 
 		if (CM == 1) {
@@ -486,6 +502,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	}
 
 	ssw_track_rows<R>(lb, snap, t * R);
+	ssw_track_unrecorded(lb);
 	int sc0, bp0, br0, sc1, bp1, br1;
 	ssw_reduce_best<G>(lb, sc0, bp0, br0, sc1, bp1, br1);
 	if (live && t == 0) {
@@ -634,7 +651,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 				outH = pk[2 * R]; outF = pk[2 * R + 1]; outC = pk[2 * R + 2];
 			}
 			SswLaneBest lb;
-			lb.best = 0; lb.pos0 = lb.pos1 = lb.row0 = lb.row1 = 0;
+			lb.best = 0; lb.pos0 = lb.pos1 = -1; lb.row0 = lb.row1 = 0;
 			SswSnap<R, false> snap;
 			ssw_snap_init<R>(snap);
 
@@ -782,6 +799,7 @@ ssw_fill_strips_kernel(const SswStripTask* __restrict__ tasks,
 				pk[2 * R] = outH; pk[2 * R + 1] = outF; pk[2 * R + 2] = outC;
 			}
 			ssw_track_rows<R>(lb, snap, s * 32 * R + lane * R);
+			ssw_track_unrecorded(lb);
 			int sc0, bp0, br0, sc1, bp1, br1;
 			ssw_reduce_best<32>(lb, sc0, bp0, br0, sc1, bp1, br1);
 			if (lane == 0) {

@@ -22,7 +22,7 @@ struct SswGridArgs {
 	int32_t n_r;         /* references */
 	int32_t n_r_pad;     /* references rounded up to a whole number of CTAs (dead items in between) */
 	int32_t word, limit;
-	int32_t pad_;
+	int32_t arm_tail;    /* > 0: best-cell rows are recorded in the last arm_tail columns of every reference only (SswItem.cend) */
 	int64_t cm_words_per_qp;
 };
 
@@ -45,7 +45,8 @@ ssw_grid_plan_kernel(SswGridArgs A, const int2* __restrict__ qp, const SswGridQ*
 	SswGridQ qb;
 	qb.off = 0; qb.len = 0; qb.lp = 0; qb.mask_len = 0;
 	if (pr.y >= 0) { qb = qt[pr.y]; it.qb.off = qb.off; it.qb.len = qb.len; it.qb.lp = qb.lp; }
-	it.ref_off = ref_off[r]; it.ref_len = ref_len[r]; it.cend = 0;
+	it.ref_off = ref_off[r]; it.ref_len = ref_len[r];
+	it.cend = (A.arm_tail > 0 && live) ? max(0, ref_len[r] - A.arm_tail) : 0;
 	it.p0 = 0; it.p1 = live ? ref_len[r] : 0; it.warm = 0; it.term_a = -1;
 	it.cm_off = live ? (int64_t)pi * A.cm_words_per_qp + cm_prefix[r] : SSW_CM_NONE;
 	items[idx] = it;

@@ -52,12 +52,15 @@ ssw_resolve_kernel(const SswAlnDesc* __restrict__ alns, int n_aln,
 		if (o_sc > sc || (o_sc == sc && (o_pos < pos || (o_pos == pos && o_row < row)))) { sc = o_sc; pos = o_pos; row = o_row; }
 	}
 	if (sc == 0) { pos = 0; row = 0; }
+	const bool unarmed = sc > 0 && pos < 0;          /* the maximum lies before the armed range of its item: no position, no row */
+	if (unarmed) { pos = 0; row = 0; }
 
 	SswFillResult r;
 	r.score = sc; r.ref = pos; r.read = row < d.read_len - 1 ? row : d.read_len - 1;
 	r.score2 = 0; r.ref2 = 0; r.overflow = 0; r.pad_[0] = r.pad_[1] = 0;
 	if (sc == 0) { r.ref = d.word ? 0 : -1; r.read = 0; }
 	if (sc >= d.limit) { r.overflow = d.word ? 2 : 1; if (!d.word) r.score = 255; }
+	else if (unarmed) r.overflow = 3;                 /* the caller re-does the pair with arm 0 */
 
 	if (SECOND && sc > 0 && !r.overflow && d.cm_off != SSW_CM_NONE) {
 		/* allowed columns: [0, e1) and [e2, refLen); smallest index of the largest value, values must be > 0 */
@@ -150,12 +153,15 @@ ssw_resolve_blocks_kernel(const SswAlnDesc* __restrict__ alns, int n_aln,
 		if (o_sc > sc || (o_sc == sc && (o_pos < pos || (o_pos == pos && o_row < row)))) { sc = o_sc; pos = o_pos; row = o_row; }
 	}
 	if (sc == 0) { pos = 0; row = 0; }
+	const bool unarmed = sc > 0 && pos < 0;          /* the maximum lies before the armed range of its item: no position, no row */
+	if (unarmed) { pos = 0; row = 0; }
 
 	SswFillResult r;
 	r.score = sc; r.ref = pos; r.read = row < d.read_len - 1 ? row : d.read_len - 1;
 	r.score2 = 0; r.ref2 = 0; r.overflow = 0; r.pad_[0] = r.pad_[1] = 0;
 	if (sc == 0) { r.ref = d.word ? 0 : -1; r.read = 0; }
 	if (sc >= d.limit) { r.overflow = d.word ? 2 : 1; if (!d.word) r.score = 255; }
+	else if (unarmed) r.overflow = 3;                 /* the caller re-does the pair with arm 0 */
 
 	int slots[SSW_REFILL_SLOTS] = {-1, -1, -1};
 	if (sc > 0 && !r.overflow && d.cm_off != SSW_CM_NONE && d.n_items > 0) {

@@ -169,6 +169,8 @@ int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t);
  *   "grid_min"      smallest full score-only grid that is planned on the device
  *   "grid_split"    grids of at least this many pairs are cut into launch groups whose records are copied back while the
  *                   next group computes (default 4 Mi pairs); "grid_group": smallest group in query pairs (default 16)
+ *   "grid_arm"      device-planned grid: record best-cell rows only in the last k columns of every reference and re-do the pairs
+ *                   whose maximum lies earlier (-1 automatic: protein-like alphabets, with a pilot group; 0 off; k > 0 fixed)
  *   "tb_maxbw"      widest band handled by the shared-memory traceback kernel
  *   "tb_spec"       band-doubling rounds of a traceback: 1 side by side (one warp per round), 0 one after the other,
  *                   -1 (default) side by side for batches too small to keep the device busy

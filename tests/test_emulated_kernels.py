@@ -258,6 +258,20 @@ def test_emulated_device_planned_grid(oracle, capfd):
     res, pool = eng.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
     exp, exp_pool, _, _, _ = C.cpu_batch(W["queries"], W["refs"], pq, pr, C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1, threads=4)
     assert C.compare_records(res, pool, exp, exp_pool) == []
+    # late arming of the best-cell bookkeeping: a tail so short that many maxima lie before it (those pairs are re-done by the general
+    # path), a generous one, and the automatic choice (pilot group first)
+    W = C.config_workload(4, n_queries=6, n_targets=41)
+    pq6, pr6 = np.repeat(np.arange(6), 41), np.tile(np.arange(41), 6)
+    eng.set_sequences(W["queries"], W["refs"])
+    exp, exp_pool, _, _, _ = C.cpu_batch(W["queries"], W["refs"], pq6, pr6, C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1, threads=4)
+    redone = []
+    for arm in (30, 250, -1, 0):
+        eng.set_option("grid_arm", arm)
+        res, pool = eng.align(C.BLOSUM50, 24, 3, 1, flag=0, mask_len=150, score_size=1)
+        assert C.compare_records(res, pool, exp, exp_pool) == [], arm
+        redone.append(eng.timing()["byte_overflows"])
+    assert redone[0] > 20 and redone[3] == 0, redone          # tail 30: most maxima lie earlier; armed everywhere: nothing to re-do
+    eng.set_option("grid_arm", -1)
     eng.set_option("grid_split", -1)
     eng.set_option("grid_group", -1)
     eng.set_option("grid_min", -1)
