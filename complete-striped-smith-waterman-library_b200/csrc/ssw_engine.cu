@@ -149,7 +149,7 @@ struct ssw_engine {
 /* fill kernel dispatch                                                                          */
 /* ------------------------------------------------------------------------------------------- */
 
-struct FillPtrs { const SswItem* items; uint32_t* cm; SswItemBest* bests; };
+struct FillPtrs { const SswItem* items; uint32_t* cm; SswItemBest* bests; bool arm = false; /* items carry late arming positions (grid path) */ };
 
 /* Warps per CTA of a forward launch with a CTA-shared profile: 8 instead of 4 when that doubles the resident warps per SM
  * (large alphabets: the profile, not the registers, limits the CTAs per SM). */
@@ -191,22 +191,27 @@ static int launch_fill(ssw_engine* e, const FillPtrs& fp, int n_items, int dir, 
 	const int8_t* mat = e->d_mat.as<int8_t>();
 	uint32_t* cm = fp.cm;
 	SswItemBest* bests = fp.bests;
-#define SSW_FILL_GO(DIR, CM, TERM, W)                                                                            \
+#define SSW_FILL_GO(DIR, CM, TERM, W, ARM)                                                                       \
 	do {                                                                                                         \
-		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM, W>;                                                     \
+		auto kern = ssw_fill_kernel<G, R, DIR, CM, TERM, W, ARM>;                                                \
 		if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem)) return -1;                           \
 		ssw_launch(kern, dim3(grid), dim3(warps * 32), smem, e->stream, items, n_items, q, r, mat, (int)P.n,     \
 		           (int)P.gap_open, (int)P.gap_extend, cm, bests, share);                                        \
 	} while (0)
 	if (dir > 0) {   /* forward: column maxima per column or per block */
 		if (warps == 8) {
-			if constexpr (R >= 16) { if (cm_mode == 2) SSW_FILL_GO(1, 2, false, 8); else SSW_FILL_GO(1, 1, false, 8); }
+			if constexpr (R >= 16) {
+				if (cm_mode == 2) SSW_FILL_GO(1, 2, false, 8, false);
+				else if (fp.arm) SSW_FILL_GO(1, 1, false, 8, true);
+				else SSW_FILL_GO(1, 1, false, 8, false);
+			}
 			else return -2;
 		}
-		else if (cm_mode == 2) SSW_FILL_GO(1, 2, false, SSW_FILL_WARPS);
-		else SSW_FILL_GO(1, 1, false, SSW_FILL_WARPS);
+		else if (cm_mode == 2) SSW_FILL_GO(1, 2, false, SSW_FILL_WARPS, false);
+		else if (fp.arm) SSW_FILL_GO(1, 1, false, SSW_FILL_WARPS, true);
+		else SSW_FILL_GO(1, 1, false, SSW_FILL_WARPS, false);
 	} else {
-		if constexpr (G == 32) SSW_FILL_GO(-1, 0, true, SSW_FILL_WARPS);   /* reverse: one alignment per warp, early termination */
+		if constexpr (G == 32) SSW_FILL_GO(-1, 0, true, SSW_FILL_WARPS, false);   /* reverse: one alignment per warp, early termination */
 		else return -2;
 	}
 #undef SSW_FILL_GO
@@ -1419,7 +1424,8 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		/* fill (items are already on the device) */
 		{
 			e->laps.start(e->stream);
-			const FillPtrs fp = {e->d_items.as<SswItem>(), e->d_colmax.as<uint32_t>(), e->d_bests.as<SswItemBest>()};
+			FillPtrs fp = {e->d_items.as<SswItem>(), e->d_colmax.as<uint32_t>(), e->d_bests.as<SswItemBest>()};
+			fp.arm = A.arm_tail > 0;
 			const int rc = dispatch_fill(e, inst, fp, (int)n_items, +1, 1, 1, P);
 			if (rc) return rc < 0 ? rc : -1;
 			e->laps.stop(e->stream, &e->timing.fill_forward_ms);

@@ -341,7 +341,9 @@ __device__ static __forceinline__ void ssw_reduce_best(const SswLaneBest& lb, in
  *      re-fills those three blocks per alignment with mode 1.  Chunks start at multiples of SSW_CM_BLOCK. */
 /* WARPS: warps per CTA.  4 by default; 8 where one CTA-shared profile is so large (protein alphabets: 64 KB at 20 rows per
  * lane) that four-warp CTAs would leave the SM with 8 resident warps -- eight warps per profile keep 16. */
-template <int G, int R, int DIR, int CM, bool TERM, int WARPS = SSW_FILL_WARPS>
+/* ARM: items may carry a late arming position (SswItem.cend, device-planned grids); a template parameter because the extra
+ * predicate per step costs the kernels that never use it 1.8 % (measured on config 2). */
+template <int G, int R, int DIR, int CM, bool TERM, int WARPS = SSW_FILL_WARPS, bool ARM = false>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == SSW_FILL_WARPS ? SSW_FILL_MINB : 2)
 ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 const int8_t* __restrict__ qcodes, const int8_t* __restrict__ refs,
@@ -428,7 +430,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 		 * no position, no snapshot, no branch.  If the item's maximum turns out to lie there (its position stays -1) the
 		 * resolve step flags the pair and it is re-done with arm 0.  Protein grids: the running maximum grows on every
 		 * column, the best cell lies in the last third of the reference for 99.99 % of the pairs. */
-		const bool unarmed = DIR > 0 && sp0 + U - 1 < it.cend;
+		const bool unarmed = ARM && DIR > 0 && sp0 + U - 1 < it.cend;
 #pragma unroll
 		for (int j = 0; j < U; ++j) {
 			/* values crossing the lane boundary */
@@ -449,7 +451,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 			const uint32_t nb = __vmaxs2(lb.best, own);
 			if (unarmed) lb.best = nb;
 			else if (nb != lb.best && maybe_counted) {
-				if (DIR > 0 && sp0 + j < it.cend) lb.best = nb;          /* the body that crosses `arm`: still before it */
+				if (ARM && DIR > 0 && sp0 + j < it.cend) lb.best = nb;   /* the body that crosses `arm`: still before it */
 				else ssw_track<R>(lb, snap, nb, Hn, sp0 + j, it.p0, it.p1);
 			}
 		}
