@@ -68,7 +68,7 @@ struct SswOptions {
 	int grid_group_qp = 16;         /* "grid_group": smallest such group, in query pairs */
 	int grid_arm = -1;              /* "grid_arm": best-cell rows of the device-planned grid are recorded in the last k columns of a reference only
 	                                 * (pairs whose maximum lies earlier are re-done): -1 automatic (protein-like alphabets: padded query
-	                                 * length / 2 + 64, switched off when a pilot group re-does more than 2 % of its pairs), 0 off, k > 0 fixed */
+	                                 * length / 2 + 64, switched off when a pilot group re-does more than 0.2 % of its pairs), 0 off, k > 0 fixed */
 	int64_t latency_cols = (int64_t)5 << 19;   /* "latency_cols": passes over at most this many reference columns (2.6 M: one wave of
 	                                            * 1,024-column items on 148 SMs) use the 32-lane instances */
 	int force_inst = -1;            /* "inst" (measurements): use this forward instance whenever it covers the query */
@@ -1372,7 +1372,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 	/* Late arming of the best-cell bookkeeping (ssw_fill.cuh): rows are recorded in the last arm_tail columns of every
 	 * reference only.  Automatic for protein-like alphabets, where the running maximum grows with every column and the
 	 * maximum of a pair lies near the end of the reference; a small pilot group goes first and the rest of the grid is
-	 * armed from column 0 again if more than 2 % of the pilot's pairs had to be re-done. */
+	 * armed from column 0 again if more than 0.2 % of the pilot's pairs had to be re-done. */
 	bool arm_on = e->opt.grid_arm > 0 || (e->opt.grid_arm < 0 && P.n > 8 && e->grid_arm_ok);
 	bool pilot_pending = arm_on && e->opt.grid_arm < 0;
 	int64_t pilot_pairs = 0;
@@ -1461,7 +1461,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 			SSW_CUDA_OK(cudaMemcpyAsync(&n_now, gb + o_cnt, 4, cudaMemcpyDeviceToHost, e->stream));
 			SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
 			pilot_pairs = (int64_t)A.n_qp * 2 * n_r;
-			if ((int64_t)n_now * 50 > pilot_pairs) { arm_on = false; e->grid_arm_ok = false; }
+			if ((int64_t)n_now * 500 > pilot_pairs) { arm_on = false; e->grid_arm_ok = false; }    /* a re-done pair costs ~400x what arming saves per pair */
 		}
 		tr.lap("grid: launch group");
 	}
