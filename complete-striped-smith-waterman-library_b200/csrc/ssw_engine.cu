@@ -1461,7 +1461,17 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 			SSW_CUDA_OK(cudaMemcpyAsync(&n_now, gb + o_cnt, 4, cudaMemcpyDeviceToHost, e->stream));
 			SSW_CUDA_OK(cudaStreamSynchronize(e->stream));
 			pilot_pairs = (int64_t)A.n_qp * 2 * n_r;
-			if ((int64_t)n_now * 500 > pilot_pairs) { arm_on = false; e->grid_arm_ok = false; }    /* a re-done pair costs ~400x what arming saves per pair */
+			if ((int64_t)n_now * 500 > pilot_pairs) {    /* a re-done pair costs ~400x what arming saves per pair */
+				/* arming does not pay for these sequences: forget the pilot (its re-do list too) and run its queries again,
+				 * armed from column 0, as the first regular group -- 1/32 of the grid is computed twice, nothing goes through
+				 * the general path */
+				arm_on = false; e->grid_arm_ok = false;
+				SSW_CUDA_OK(cudaMemsetAsync(gb + o_cnt, 0, 256, e->stream));
+				groups.pop_back();
+				k = k_first;
+				tr.lap("grid: pilot group rejected");
+				continue;
+			}
 		}
 		tr.lap("grid: launch group");
 	}

@@ -272,6 +272,22 @@ def test_emulated_device_planned_grid(oracle, capfd):
         redone.append(eng.timing()["byte_overflows"])
     assert redone[0] > 20 and redone[3] == 0, redone          # tail 30: most maxima lie earlier; armed everywhere: nothing to re-do
     eng.set_option("grid_arm", -1)
+    # automatic arming where it cannot pay: short queries inside long targets (the best cell lies anywhere): the pilot group is
+    # rejected and recomputed armed from column 0 -- nothing is re-done by the general path
+    rng2 = np.random.default_rng(99)
+    tq = [rng2.integers(0, 20, size=40).astype(np.int8) for _ in range(6)]
+    tt = []
+    for k in range(30):
+        t = rng2.integers(0, 20, size=260).astype(np.int8)
+        a = int(rng2.integers(0, 200))
+        t[a: a + 40] = tq[k % 6]
+        tt.append(t)
+    eng.set_sequences(tq, tt)
+    res, pool = eng.align(C.BLOSUM50, 24, 12, 2, flag=0, mask_len=20, score_size=1)
+    exp, exp_pool, _, _, _ = C.cpu_batch(tq, tt, np.repeat(np.arange(6), 30), np.tile(np.arange(30), 6), C.BLOSUM50, 24, 12, 2, flag=0, mask_len=20,
+                                        score_size=1, threads=4)
+    assert C.compare_records(res, pool, exp, exp_pool) == []
+    assert eng.timing()["byte_overflows"] == 0
     eng.set_option("grid_split", -1)
     eng.set_option("grid_group", -1)
     eng.set_option("grid_min", -1)
