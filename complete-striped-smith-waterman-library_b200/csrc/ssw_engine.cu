@@ -68,7 +68,7 @@ struct SswOptions {
 	int grid_group_qp = 16;         /* "grid_group": smallest such group, in query pairs */
 	int grid_arm = -1;              /* "grid_arm": best-cell rows of the device-planned grid are recorded in the last k columns of a reference only
 	                                 * (pairs whose maximum lies earlier are re-done): -1 automatic (protein-like alphabets: padded query
-	                                 * length / 2 + 64, switched off when a pilot group re-does more than 0.2 % of its pairs), 0 off, k > 0 fixed */
+	                                 * length / 4 + 64, switched off when a pilot group re-does more than 0.2 % of its pairs), 0 off, k > 0 fixed */
 	int64_t latency_cols = (int64_t)5 << 19;   /* "latency_cols": passes over at most this many reference columns (2.6 M: one wave of
 	                                            * 1,024-column items on 148 SMs) use the 32-lane instances */
 	int force_inst = -1;            /* "inst" (measurements): use this forward instance whenever it covers the query */
@@ -1403,7 +1403,7 @@ static int grid_scores(ssw_engine* e, const ssw_batch_params& P, const Sem& S, i
 		if (arm_on) {
 			int lp_max = 0;
 			for (const int2& pr : qps) { lp_max = std::max(lp_max, qt[pr.x].lp); if (pr.y >= 0) lp_max = std::max(lp_max, qt[pr.y].lp); }
-			A.arm_tail = e->opt.grid_arm > 0 ? e->opt.grid_arm : lp_max / 2 + 64;
+			A.arm_tail = e->opt.grid_arm > 0 ? e->opt.grid_arm : lp_max / 4 + 64;
 		}
 		const int64_t n_items = (int64_t)A.n_qp * n_r_pad, n_desc = (int64_t)A.n_qp * n_r * 2;
 		if (n_items > 0x7fffffff || n_desc > 0x7fffffff) return 0;
