@@ -366,7 +366,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!strcmp(name, "grid_min")) { o.grid_min_pairs = value < 0 ? 32768 : (int)value; return 0; }
 	if (!strcmp(name, "inst")) { o.force_inst = (int)value; return 0; }       /* index into kInst */
 	if (!strcmp(name, "super")) { o.strip_super = value >= 64 ? (int)(value + 7) / 8 * 8 : SSW_STRIP_SUPER; return 0; }
-	if (!strcmp(name, "tb_spec")) { o.tb_spec = value < 0 ? -1 : (value ? 1 : 0); return 0; }
+	if (!strcmp(name, "tb_spec")) { o.tb_spec = value < 0 ? -1 : (int)value; return 0; }      /* > 1: on, rounds up to that many columns */
 	if (!strcmp(name, "tb_maxbw")) { o.tb_maxbw = value < 0 ? SSW_TBP_MAXBW : (int)std::min<int64_t>(value, SSW_TBP_MAXBW); return 0; }
 	fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name);
 	return -1;

@@ -628,12 +628,13 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 	 * issue, not by the latency of a row, and the speculative rounds make it slower (74 -> 86 ms); a single 10 kbp read
 	 * (one ssw_align call) is pure latency and gains.  Automatic: on for small batches only. */
 	const bool spec_on = tb_spec > 0 || (tb_spec < 0 && tasks.size() <= 256);
-	auto spec_rounds = [tb_maxbw, spec_on](const SswTbTask& t) -> int {
+	const int tb_spec_w = tb_spec > 1 ? tb_spec : 129;          /* "tb_spec" values above 1: widest row (columns) of a speculated round */
+	auto spec_rounds = [tb_maxbw, spec_on, tb_spec_w](const SswTbTask& t) -> int {
 		if (!spec_on) return 1;
 		const int len = std::max(t.ref_len, t.read_len);
 		int nw = 0, bw = t.bw;
 		while (nw < SSW_TBS_MAXW && bw <= tb_maxbw) {
-			if (nw >= 2 && 2 * bw + 1 > 129) break;
+			if (nw >= 1 && 2 * bw + 1 > tb_spec_w) break;      /* only rounds of at most tb_spec_w columns ride along with the first one */
 			++nw;
 			if (!(2 * bw <= len)) break;
 			bw *= 2;
