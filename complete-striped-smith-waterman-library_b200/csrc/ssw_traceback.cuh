@@ -626,8 +626,9 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 	 * a task that needs only the first loses little. */
 	/* Measured on a B200 (config 5, 1,000 reads of 10 kbp): with a thousand tasks in flight the phase is bound by instruction
 	 * issue, not by the latency of a row, and the speculative rounds make it slower (74 -> 86 ms); a single 10 kbp read
-	 * (one ssw_align call) is pure latency and gains.  Automatic: on for small batches only. */
-	const bool spec_on = tb_spec > 0 || (tb_spec < 0 && tasks.size() <= 256);
+	 * (one ssw_align call) is pure latency and gains.  Automatic: on for a handful of tasks only (slices of 250 tasks were
+	 * still slower with it). */
+	const bool spec_on = tb_spec > 0 || (tb_spec < 0 && tasks.size() <= 8);
 	const int tb_spec_w = tb_spec > 1 ? tb_spec : 129;          /* "tb_spec" values above 1: widest row (columns) of a speculated round */
 	auto spec_rounds = [tb_maxbw, spec_on, tb_spec_w](const SswTbTask& t) -> int {
 		if (!spec_on) return 1;

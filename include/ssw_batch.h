@@ -174,7 +174,7 @@ int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t);
  *   "tb_maxbw"      widest band handled by the shared-memory traceback kernel
  *   "tb_spec"       band-doubling rounds of a traceback: 0 one after the other, 1 side by side (one warp per round; rounds of at most
  *                   129 columns ride along with the first), w > 1 the same with rounds of up to w columns,
- *                   -1 (default) side by side for batches too small to keep the device busy
+ *                   -1 (default) side by side for a handful of tasks only (a lone call)
  */
 int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value);
 
