@@ -59,8 +59,14 @@ static const int kNumFwd = 10;
 static const int kNumInst = (int)(sizeof(kInst) / sizeof(kInst[0]));
 
 /* Tuning knobs ("ssw_engine_set_option"); every engine has its own copy (helper engines get their parent's). */
+#define SSW_MAX_SLICES 8
 struct SswOptions {
-	int slices = 0;                 /* "slices": 0 automatic, 1 never slice a batch over helper engines, 2/3 forced (tests) */
+	int slices = 0;                 /* "slices": 0 automatic, 1 never slice a batch over helper engines, 2..8 forced (tests, measurements) */
+	int slice_taper = 0;            /* "slice_taper": 0 equal slices; t in 1..99: every slice holds t % of the pairs of the one before it (the
+	                                 * traceback of the last slice is not hidden under any fill: a short last slice shortens that tail) */
+	int slice_prio = 0;             /* "slice_prio": 1 = the streams of earlier slices get a higher priority (pending CTAs of a slice's reverse
+	                                 * pass / traceback are dispatched before pending fill CTAs of later slices) */
+	int tail_spec = 0;              /* "tail_spec": 1 = the last slice runs its traceback with the speculative kernel (it runs on an idle device) */
 	int strip_parts = 0;            /* "parts": 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
 	int strip_super = SSW_STRIP_SUPER;   /* "super": columns per super-block of the strip kernel (tests) */
 	int grid_min_pairs = 32768;     /* "grid_min": smaller grids use the general path */
@@ -122,7 +128,8 @@ struct ssw_engine {
 	SswDevBuf d_rf_items, d_rf_bests, d_rf_blk, d_rf_cm;     /* block-maximum mode: re-fill items, their (unused) bests, block ids, column maxima */
 	SswStagedD2H staged;
 	cudaStream_t side[3] = {nullptr, nullptr, nullptr};     /* traceback launches of different kernel shapes run side by side */
-	ssw_engine* kids[3] = {nullptr, nullptr, nullptr};      /* helper engines of the sliced path (views of this engine's sequences) */
+	ssw_engine* kids[SSW_MAX_SLICES] = {};                  /* helper engines of the sliced path (views of this engine's sequences) */
+	int prio = 0;                                            /* stream priority of this engine's streams (0: default) */
 	bool is_kid = false;
 	SswOptions opt;
 	ssw_engine_timing timing;
@@ -309,6 +316,29 @@ static int fill_occupancy(int inst, int n)
 /* engine life cycle                                                                              */
 /* ------------------------------------------------------------------------------------------- */
 
+/* a non-blocking stream of priority `prio` (CUDA: lower numbers are served first; 0 = default) */
+static cudaError_t ssw_make_stream(cudaStream_t* st, int prio)
+{
+#ifndef SSW_CPU_EMU
+	if (prio != 0) return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio);
+#endif
+	(void)prio;
+	return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+}
+
+/* give all streams of a helper engine the priority `prio` (they are idle: called between batches) */
+static int ssw_engine_set_priority(ssw_engine* e, int prio)
+{
+	if (e->prio == prio) return 0;
+	for (cudaStream_t& st : e->side) if (st) { cudaStreamDestroy(st); st = nullptr; }
+	cudaStream_t fresh = nullptr;
+	if (ssw_make_stream(&fresh, prio) != cudaSuccess) return -1;
+	if (e->stream) cudaStreamDestroy(e->stream);
+	e->stream = fresh;
+	e->prio = prio;
+	return 0;
+}
+
 extern "C" ssw_engine* ssw_engine_create(int device)
 {
 	int count = 0;
@@ -353,7 +383,10 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	if (!name) return -1;
 	if (!e) return ssw_default_engines_option(name, value);
 	SswOptions& o = e->opt;
-	if (!strcmp(name, "slices")) { o.slices = value >= 1 && value <= 3 ? (int)value : 0; return 0; }
+	if (!strcmp(name, "slices")) { o.slices = value >= 1 && value <= SSW_MAX_SLICES ? (int)value : 0; return 0; }
+	if (!strcmp(name, "slice_taper")) { o.slice_taper = value >= 1 && value <= 99 ? (int)value : 0; return 0; }
+	if (!strcmp(name, "slice_prio")) { o.slice_prio = value > 0 ? 1 : 0; return 0; }
+	if (!strcmp(name, "tail_spec")) { o.tail_spec = value > 0 ? 1 : 0; return 0; }
 	if (!strcmp(name, "latency_cols")) { o.latency_cols = value < 0 ? ((int64_t)5 << 19) : value; return 0; }
 	if (!strcmp(name, "parts")) { o.strip_parts = value == 1 || value == 2 || value == 4 ? (int)value : 0; return 0; }
 	if (!strcmp(name, "small_chunk")) { o.small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
@@ -1639,6 +1672,7 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 	phase.lap("general: records");
 	/* ---- P3 ---- */
 	if (!tb.empty()) {
+		if (e->prio) for (cudaStream_t& st : e->side) if (!st) SSW_CUDA_OK(ssw_make_stream(&st, e->prio));
 		rc = ssw_traceback_run(e->stream, e->side, tb, e->d_q.as<int8_t>(), e->d_r.as<int8_t>(), e->d_mat.as<int8_t>(), P.n,
 		                       P.gap_open, P.gap_extend, &e->d_tb, &e->timing.traceback_ms, &e->timing.other_launches, e->opt.tb_maxbw, e->opt.tb_spec,
 		                       [&](size_t i, const uint32_t* words, int32_t len, int failed) -> int {
@@ -1715,9 +1749,25 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 			/* pool: worst-case sized, most of it never touched -- uninitialised storage, not a zero-filled vector */
 			struct Slice { int64_t lo, hi, used, cap; int rc; std::unique_ptr<uint32_t[]> pool; };
 			std::vector<Slice> sl((size_t)slices);
+			/* slice boundaries: equal parts, or every slice `slice_taper` % of the one before it */
+			std::vector<int64_t> cut((size_t)slices + 1, 0);
+			{
+				std::vector<double> w((size_t)slices, 1.0);
+				if (e->opt.slice_taper > 0) for (int k = 1; k < slices; ++k) w[k] = w[k - 1] * (double)e->opt.slice_taper / 100.0;
+				double tot = 0, acc = 0;
+				for (double x : w) tot += x;
+				for (int k = 0; k < slices; ++k) {
+					acc += w[k];
+					cut[k + 1] = k + 1 == slices ? n_pairs : std::max<int64_t>(cut[k] + 1, std::min<int64_t>(n_pairs - (slices - 1 - k), (int64_t)((double)n_pairs * acc / tot)));
+				}
+			}
+			int prio_least = 0, prio_greatest = 0;
+#ifndef SSW_CPU_EMU
+			if (e->opt.slice_prio) SSW_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+#endif
 			for (int k = 0; k < slices; ++k) {
 				Slice& s = sl[k];
-				s.lo = n_pairs * k / slices; s.hi = n_pairs * (k + 1) / slices; s.used = 0; s.rc = 0;
+				s.lo = cut[k]; s.hi = cut[k + 1]; s.used = 0; s.rc = 0;
 				int64_t cap = 0;
 				for (int64_t p = s.lo; p < s.hi; ++p) {
 					const int32_t q = pair_query[p], r = pair_ref[p];
@@ -1733,6 +1783,9 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 				kid->padded_n = e->padded_n; kid->from_text = true;     /* no host copy: the padded references are the parent's */
 				kid->d_q.borrow(e->d_q); kid->d_r.borrow(e->d_r);
 				kid->opt = e->opt;
+				if (e->opt.tail_spec && k == slices - 1 && kid->opt.tb_spec < 0) kid->opt.tb_spec = 1;
+				/* earlier slices first: the last slice keeps the default priority */
+				if (ssw_engine_set_priority(kid, e->opt.slice_prio ? std::max(prio_greatest, prio_least - (slices - 1 - k)) : 0)) return -1;
 			}
 			auto work = [&](int k) {
 				Slice& s = sl[k];

@@ -319,14 +319,27 @@ __device__ static __forceinline__ void ssw_tb_walk(SswTbTask& T, SswTbTask* slot
 	constexpr unsigned FULL = 0xffffffffu;
 	const int bw = T.bw, W = 2 * bw + 1, ql = T.read_len;
 	const long long dir_cells = (long long)W * ql;
-	const int rows_per_block = max(1, (stage_bytes - 8) / W);
+	const int rows_per_block = max(1, (stage_bytes - 48) / W);     /* 8 spare bytes + up to 2 x 15 bytes of alignment slack */
 	int wi = T.max_i, wj = T.max_j, e = 0, l = 0, state = 2, op = 0, prev = 0;
 	int bad = 0, more = (wi >= 0 && wj > 0) ? 1 : 0;
 	while (more) {
 		const int i_lo = max(0, wi - rows_per_block + 1);
-		const long long base = (long long)W * i_lo - 1;               /* first staged cell: x == -1 of the lowest row */
+		const long long want = (long long)W * i_lo - 1;               /* first cell the walk may read: x == -1 of the lowest row */
 		const long long last = min((long long)W * (wi + 1), dir_cells);   /* last staged cell: x == 2bw+1 of the top row */
-		for (long long c = base + lane; c <= last; c += 32) stage[c - base] = dir[c];
+		/* 16 bytes per lane and step: the block starts at the 16-byte boundary at or below `want` (never below this task's
+		 * own cells: they begin on such a boundary) and ends with the 16-byte word that holds `last` (inside the padded area) */
+		const long long base = want - (long long)(reinterpret_cast<uintptr_t>(dir + want) & 15);
+		{
+			const uint4* src = reinterpret_cast<const uint4*>(dir + base);
+			uint4* dst = reinterpret_cast<uint4*>(stage);
+			const int n16 = (int)((last - base) / 16) + 1;
+			int k = lane;
+			for (; k + 96 < n16; k += 128) {
+				const uint4 a = src[k], b = src[k + 32], c = src[k + 64], d = src[k + 96];
+				dst[k] = a; dst[k + 32] = b; dst[k + 64] = c; dst[k + 96] = d;
+			}
+			for (; k < n16; k += 32) dst[k] = src[k];
+		}
 		__syncwarp();
 		if (lane == 0) {
 			more = 0;

@@ -141,8 +141,9 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
             got["cigar"] = [int(x) for x in base_pool[r["cigar_off"]: r["cigar_off"] + r["cigar_len"]]] if r["cigar_off"] >= 0 else []
             assert C.diff_results(got, exp) == [], k
             k += 1
-    for slices in (3,):
+    for slices, taper in ((3, 0), (5, 60)):      # equal slices; five slices, each 60 % of the one before it
         eng.set_option("slices", slices)
+        eng.set_option("slice_taper", taper)
         res, pool = eng.align(mat, 5, 3, 1, flag=0x0f, filterd=32767, mask_len=100, score_size=2)
         assert len(pool) == len(base_pool)
         for a, b in zip(res, base_res):
@@ -151,6 +152,7 @@ def test_emulated_long_queries_strip_pipeline(oracle, capfd):
             if a["cigar_len"] > 0:
                 assert list(pool[a["cigar_off"]: a["cigar_off"] + a["cigar_len"]]) == list(base_pool[b["cigar_off"]: b["cigar_off"] + b["cigar_len"]])
     eng.set_option("slices", 0)
+    eng.set_option("slice_taper", 0)
     eng.set_option("super", 0)
     eng.close()
 
