@@ -125,7 +125,7 @@ int ssw_default_engines_option(const char* name, int64_t value)
 	std::lock_guard<std::mutex> lock(g_mu);
 	if (g_pool.empty()) {
 		/* validate the name on a throw-away basis: an unknown option must fail now, not at the first ssw_align */
-		static const char* known[] = {"slices", "slice_taper", "slice_prio", "tail_spec", "latency_cols", "parts", "small_chunk", "chunk", "cm_block", "cm_budget_mb", "grid_min", "inst", "super", "tb_maxbw", "tb_spec", "grid_split", "grid_group", "grid_arm"};
+		static const char* known[] = {"slices", "slice_taper", "carve", "latency_cols", "parts", "small_chunk", "chunk", "cm_block", "cm_budget_mb", "grid_min", "inst", "super", "tb_maxbw", "tb_spec", "grid_split", "grid_group", "grid_arm"};
 		bool ok = false;
 		for (const char* k : known) if (!strcmp(k, name)) ok = true;
 		if (!ok) { fprintf(stderr, "[libssw-b200] unknown option '%s'\n", name); return -1; }

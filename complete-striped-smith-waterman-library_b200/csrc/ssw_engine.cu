@@ -64,9 +64,8 @@ struct SswOptions {
 	int slices = 0;                 /* "slices": 0 automatic, 1 never slice a batch over helper engines, 2..8 forced (tests, measurements) */
 	int slice_taper = 0;            /* "slice_taper": 0 equal slices; t in 1..99: every slice holds t % of the pairs of the one before it (the
 	                                 * traceback of the last slice is not hidden under any fill: a short last slice shortens that tail) */
-	int slice_prio = 0;             /* "slice_prio": 1 = the streams of earlier slices get a higher priority (pending CTAs of a slice's reverse
-	                                 * pass / traceback are dispatched before pending fill CTAs of later slices) */
-	int tail_spec = 0;              /* "tail_spec": 1 = the last slice runs its traceback with the speculative kernel (it runs on an idle device) */
+	int carve = 1;                  /* "carve": 1 = the kernels of the long-read phases (strip fills, traceback) ask for the largest shared-memory
+	                                 * carve-out, so that their launches can share SMs (0: the driver's choice per launch; measurements) */
 	int strip_parts = 0;            /* "parts": 0 automatic, 1 never split the strips of a task, 2/4 forced (tests) */
 	int strip_super = SSW_STRIP_SUPER;   /* "super": columns per super-block of the strip kernel (tests) */
 	int grid_min_pairs = 32768;     /* "grid_min": smaller grids use the general path */
@@ -129,7 +128,6 @@ struct ssw_engine {
 	SswStagedD2H staged;
 	cudaStream_t side[3] = {nullptr, nullptr, nullptr};     /* traceback launches of different kernel shapes run side by side */
 	ssw_engine* kids[SSW_MAX_SLICES] = {};                  /* helper engines of the sliced path (views of this engine's sequences) */
-	int prio = 0;                                            /* stream priority of this engine's streams (0: default) */
 	bool is_kid = false;
 	SswOptions opt;
 	ssw_engine_timing timing;
@@ -316,29 +314,6 @@ static int fill_occupancy(int inst, int n)
 /* engine life cycle                                                                              */
 /* ------------------------------------------------------------------------------------------- */
 
-/* a non-blocking stream of priority `prio` (CUDA: lower numbers are served first; 0 = default) */
-static cudaError_t ssw_make_stream(cudaStream_t* st, int prio)
-{
-#ifndef SSW_CPU_EMU
-	if (prio != 0) return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio);
-#endif
-	(void)prio;
-	return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
-}
-
-/* give all streams of a helper engine the priority `prio` (they are idle: called between batches) */
-static int ssw_engine_set_priority(ssw_engine* e, int prio)
-{
-	if (e->prio == prio) return 0;
-	for (cudaStream_t& st : e->side) if (st) { cudaStreamDestroy(st); st = nullptr; }
-	cudaStream_t fresh = nullptr;
-	if (ssw_make_stream(&fresh, prio) != cudaSuccess) return -1;
-	if (e->stream) cudaStreamDestroy(e->stream);
-	e->stream = fresh;
-	e->prio = prio;
-	return 0;
-}
-
 extern "C" ssw_engine* ssw_engine_create(int device)
 {
 	int count = 0;
@@ -385,8 +360,7 @@ extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t va
 	SswOptions& o = e->opt;
 	if (!strcmp(name, "slices")) { o.slices = value >= 1 && value <= SSW_MAX_SLICES ? (int)value : 0; return 0; }
 	if (!strcmp(name, "slice_taper")) { o.slice_taper = value >= 1 && value <= 99 ? (int)value : 0; return 0; }
-	if (!strcmp(name, "slice_prio")) { o.slice_prio = value > 0 ? 1 : 0; return 0; }
-	if (!strcmp(name, "tail_spec")) { o.tail_spec = value > 0 ? 1 : 0; return 0; }
+	if (!strcmp(name, "carve")) { o.carve = value != 0 ? 1 : 0; return 0; }
 	if (!strcmp(name, "latency_cols")) { o.latency_cols = value < 0 ? ((int64_t)5 << 19) : value; return 0; }
 	if (!strcmp(name, "parts")) { o.strip_parts = value == 1 || value == 2 || value == 4 ? (int)value : 0; return 0; }
 	if (!strcmp(name, "small_chunk")) { o.small_chunk = value < 0 ? 0 : (value + 3) / 4 * 4; return 0; }
@@ -904,6 +878,7 @@ static int run_strips(ssw_engine* e, const ssw_batch_params& P, const std::vecto
 		do {                                                                                                            \
 			auto kern = ssw_fill_strips_kernel<SSW_STRIP_R, DIR, TERM, SPLIT>;                                          \
 			if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem)) return -1;                              \
+			if (e->opt.carve && ssw_prefer_max_smem(reinterpret_cast<const void*>(kern))) return -1;                    \
 			ssw_launch(kern, dim3((unsigned)(tasks.size() * (size_t)parts)), dim3(nw * 32), smem, e->stream, (const SswStripTask*)e->d_items.as<SswStripTask>(), \
 			           (const int8_t*)e->d_q.as<int8_t>(), (const int8_t*)e->d_r.as<int8_t>(), (const int8_t*)e->d_mat.as<int8_t>(), (int)P.n, \
 			           (int)P.gap_open, (int)P.gap_extend, e->d_colmax.as<uint32_t>(), e->d_bnd.as<uint32_t>(), e->d_park.as<uint32_t>(), \
@@ -1672,9 +1647,8 @@ static int align_general(ssw_engine* e, const ssw_batch_params& P, const Sem& S,
 	phase.lap("general: records");
 	/* ---- P3 ---- */
 	if (!tb.empty()) {
-		if (e->prio) for (cudaStream_t& st : e->side) if (!st) SSW_CUDA_OK(ssw_make_stream(&st, e->prio));
 		rc = ssw_traceback_run(e->stream, e->side, tb, e->d_q.as<int8_t>(), e->d_r.as<int8_t>(), e->d_mat.as<int8_t>(), P.n,
-		                       P.gap_open, P.gap_extend, &e->d_tb, &e->timing.traceback_ms, &e->timing.other_launches, e->opt.tb_maxbw, e->opt.tb_spec,
+		                       P.gap_open, P.gap_extend, &e->d_tb, &e->timing.traceback_ms, &e->timing.other_launches, e->opt.tb_maxbw, e->opt.carve != 0, e->opt.tb_spec,
 		                       [&](size_t i, const uint32_t* words, int32_t len, int failed) -> int {
 			ssw_batch_result& r = results[tb_pair[i]];
 			if (failed) { r.flag = 1; return 0; }                           /* ssw.c:968 */
@@ -1727,15 +1701,17 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 	/* Long reads with CIGARs: the banded traceback is a set of long serial chains that leaves most of the device idle, and
 	 * the strip fills before it are throughput-bound.  The batch is cut into slices that run on helper engines (own stream
 	 * and scratch, views of this engine's sequences) from as many host threads, so that one slice's traceback runs under
-	 * the fills of the others (config 5: 329 -> 288 ms with three slices). */
+	 * the fills of the others (config 5: 329 -> 288 ms with three slices).  A fill CTA takes all registers of an SM, so the
+	 * overlap is by SMs, not by issue slots: traceback CTAs move in where fill CTAs retire. */
 	{
 		int slices = 1;
+		bool auto_slices = false;
 		if (!e->is_kid && e->opt.slices != 1 && (P.flag & 7) != 0 && P.gap_open > P.gap_extend) {
 			int64_t qsum = 0;
 			const int64_t probe = std::min<int64_t>(n_pairs, 64);
 			for (int64_t p = 0; p < probe; ++p) { const int32_t q = pair_query ? pair_query[p] : (int32_t)(p / e->n_r); if (q >= 0 && q < e->n_q) qsum += e->q_off[q + 1] - e->q_off[q]; }
 			if (e->opt.slices > 1) slices = e->opt.slices;
-			else if (n_pairs >= 96 && qsum / probe >= 2000) slices = 3;
+			else if (n_pairs >= 96 && qsum / probe >= 2000) { slices = n_pairs >= 512 ? 6 : 3; auto_slices = true; }
 			slices = (int)std::min<int64_t>(slices, n_pairs);
 		}
 		if (slices > 1) {
@@ -1753,7 +1729,10 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 			std::vector<int64_t> cut((size_t)slices + 1, 0);
 			{
 				std::vector<double> w((size_t)slices, 1.0);
-				if (e->opt.slice_taper > 0) for (int k = 1; k < slices; ++k) w[k] = w[k - 1] * (double)e->opt.slice_taper / 100.0;
+				/* automatic: six slices, each 80 % of the one before it (the last slice's traceback is not hidden under any fill;
+				 * config 5: 282 ms with three equal slices, 277 ms like this) */
+				const int taper = e->opt.slice_taper > 0 ? e->opt.slice_taper : (auto_slices && slices == 6 ? 80 : 0);
+				if (taper > 0) for (int k = 1; k < slices; ++k) w[k] = w[k - 1] * (double)taper / 100.0;
 				double tot = 0, acc = 0;
 				for (double x : w) tot += x;
 				for (int k = 0; k < slices; ++k) {
@@ -1761,10 +1740,6 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 					cut[k + 1] = k + 1 == slices ? n_pairs : std::max<int64_t>(cut[k] + 1, std::min<int64_t>(n_pairs - (slices - 1 - k), (int64_t)((double)n_pairs * acc / tot)));
 				}
 			}
-			int prio_least = 0, prio_greatest = 0;
-#ifndef SSW_CPU_EMU
-			if (e->opt.slice_prio) SSW_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-#endif
 			for (int k = 0; k < slices; ++k) {
 				Slice& s = sl[k];
 				s.lo = cut[k]; s.hi = cut[k + 1]; s.used = 0; s.rc = 0;
@@ -1783,9 +1758,6 @@ static int engine_align_impl(ssw_engine* e, const ssw_batch_params* params,
 				kid->padded_n = e->padded_n; kid->from_text = true;     /* no host copy: the padded references are the parent's */
 				kid->d_q.borrow(e->d_q); kid->d_r.borrow(e->d_r);
 				kid->opt = e->opt;
-				if (e->opt.tail_spec && k == slices - 1 && kid->opt.tb_spec < 0) kid->opt.tb_spec = 1;
-				/* earlier slices first: the last slice keeps the default priority */
-				if (ssw_engine_set_priority(kid, e->opt.slice_prio ? std::max(prio_greatest, prio_least - (slices - 1 - k)) : 0)) return -1;
 			}
 			auto work = [&](int k) {
 				Slice& s = sl[k];

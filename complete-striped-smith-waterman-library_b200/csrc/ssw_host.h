@@ -84,6 +84,29 @@ inline int ssw_ensure_dyn_smem(const void* fn, size_t smem)
 	return 0;
 }
 
+/* Ask for the largest shared-memory carve-out for a kernel, once per (device, kernel).  An SM's L1 / shared-memory split can
+ * only change while the SM is idle, so launches whose carve-outs differ do not share an SM: the traceback launches of one
+ * round (same kernel, row rings of 16 / 32 / 64 KB per CTA) started up to 18 ms apart (%globaltimer of the tasks, config 5)
+ * although all their CTAs would have fitted at once.  With one carve-out for every kernel of the long-read phases (traceback,
+ * strip fills) their CTAs go wherever registers and shared memory are free. */
+inline int ssw_prefer_max_smem(const void* fn)
+{
+#ifndef SSW_CPU_EMU
+	static std::mutex mu;
+	static std::map<std::pair<int, const void*>, bool> done;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	std::lock_guard<std::mutex> lock(mu);
+	bool& d = done[std::make_pair(dev, fn)];
+	if (d) return 0;
+	if (cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) return -1;
+	d = true;
+#else
+	(void)fn;
+#endif
+	return 0;
+}
+
 /* free memory of the current device, re-read only after one of our buffers was (re)allocated */
 inline size_t ssw_free_device_bytes()
 {

@@ -36,7 +36,12 @@
 #include "ssw_common.cuh"
 #include "ssw_host.h"
 
+#ifndef SSW_TB_WARPS
 #define SSW_TB_WARPS 4
+#endif
+#ifndef SSW_TB_PRE
+#define SSW_TB_PRE 1                      /* scores of a row's first group are looked up ahead of the row */
+#endif
 #define SSW_TB_THREADS (SSW_TB_WARPS * 32)
 #define SSW_TB_NEGINF (-(1 << 30))       /* INT32_MIN / 2, ssw.c:608 */
 
@@ -54,8 +59,19 @@ struct SswTbTask {
 	int64_t row_off;     /* int32 offset of this task's 4 row buffers */
 	int64_t cig_off;     /* word offset of this task's CIGAR buffer */
 	int64_t dbg_fill, dbg_walk, dbg_score;   /* clock64 deltas of the last round (diagnostics, SSW_TRACE) */
+	int64_t dbg_t0;                          /* %globaltimer (ns) when the task's warp started */
 };
 
+__device__ static __forceinline__ int64_t ssw_globaltimer()
+{
+#ifdef SSW_CPU_EMU
+	return 0;
+#else
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return (int64_t)t;
+#endif
+}
 __device__ static __forceinline__ uint32_t ssw_tb_pack(uint32_t len, uint32_t op) { return (len << 4) | op; }  /* op: M0 I1 D2 */
 
 /* Decide whether the band must be doubled (ssw.c:678-679); if not, walk the traceback (ssw.c:683-762) from the
@@ -154,10 +170,10 @@ __device__ static __forceinline__ void ssw_tb_tile(bool act, int i, int j, int b
  * (the long chain of dependent shuffles) are independent instruction streams the scheduler can interleave; only the
  * F carry from tile to tile is serial, and that is one max per tile.  A row of the band then costs about one tile's
  * latency instead of NT. */
-template <int NT>
+template <int NT, bool LAST>
 __device__ static __forceinline__ void ssw_tb_tiles(const bool (&act)[NT], int i, const int (&j)[NT], int beg, int lane,
                                                    const int (&Hup)[NT], const int (&Eup)[NT], const int (&Hdg)[NT], const int (&s)[NT],
-                                                   int gapO, int gapE, int g, int& carryF, int& carryH, int& carryFp,
+                                                   int gapO, int gapE, int g, int& carryF, int& carryFp,
                                                    int (&Hv)[NT], int (&Ev)[NT], int (&dirb)[NT], int span)
 {
 	constexpr unsigned FULL = 0xffffffffu;
@@ -184,43 +200,49 @@ __device__ static __forceinline__ void ssw_tb_tiles(const bool (&act)[NT], int i
 			if (lane >= d) P[t] = max(P[t], o - d * g);
 		}
 	}
+	/* Shuffles cost this kernel its time (a warp's shuffles do not overlap: measured, a radix-4 scan with 7 independent
+	 * shuffles instead of 5 dependent ones is 35 % slower), so only the ones that are needed are issued:
+	 *  - df5 needs F of the left neighbour only: F(j) = max(H(j-1) - gapO, F(j-1) - gapE) is what the scan computes
+	 *    (with Y for H and g for gapE: the same value in both gap regimes), hence
+	 *    H(j-1) - gapO > F(j-1) - gapE  <=>  F(j) > F(j-1) - gapE, and H of the neighbour is never fetched;
+	 *  - the carries out of the last tile of a row (LAST) are never read. */
 	int Pm1[NT], P31[NT], cF[NT], Fv[NT];
 #pragma unroll
-	for (int t = 0; t < NT; ++t) { Pm1[t] = __shfl_up_sync(FULL, P[t], 1); P31[t] = __shfl_sync(FULL, P[t], 31); }
+	for (int t = 0; t < NT; ++t) {
+		Pm1[t] = __shfl_up_sync(FULL, P[t], 1);
+		P31[t] = (LAST && t == NT - 1) ? 0 : __shfl_sync(FULL, P[t], 31);
+	}
 	cF[0] = carryF;
 #pragma unroll
 	for (int t = 1; t < NT; ++t) cF[t] = max(P31[t - 1], cF[t - 1] - 32 * g);
-	carryF = max(P31[NT - 1], cF[NT - 1] - 32 * g);
-	int H31[NT], F31[NT], Hl[NT], Fl[NT];
+	if (!LAST) carryF = max(P31[NT - 1], cF[NT - 1] - 32 * g);
+	int F31[NT], Fl[NT];
 #pragma unroll
 	for (int t = 0; t < NT; ++t) {
 		Fv[t] = lane == 0 ? cF[t] : max(Pm1[t], cF[t] - lane * g);
 		Hv[t] = Y[t] > Fv[t] ? Y[t] : Fv[t];
-		H31[t] = __shfl_sync(FULL, Hv[t], 31);
-		F31[t] = __shfl_sync(FULL, Fv[t], 31);
-		Hl[t] = __shfl_up_sync(FULL, Hv[t], 1);
+		F31[t] = (LAST && t == NT - 1) ? 0 : __shfl_sync(FULL, Fv[t], 31);
 		Fl[t] = __shfl_up_sync(FULL, Fv[t], 1);
 	}
 #pragma unroll
 	for (int t = 0; t < NT; ++t) {
-		if (lane == 0) { Hl[t] = t == 0 ? carryH : H31[t - 1]; Fl[t] = t == 0 ? carryFp : F31[t - 1]; }
-		const int df5 = j[t] == beg ? 1 : ((Hl[t] - gapO > Fl[t] - gapE) ? 1 : 0);
+		if (lane == 0) Fl[t] = t == 0 ? carryFp : F31[t - 1];
+		const int df5 = j[t] == beg ? 1 : ((Fv[t] > Fl[t] - gapE) ? 1 : 0);
 		const int f1 = Fv[t] > 0 ? Fv[t] : 0;
 		const int T1 = e1[t] > f1 ? e1[t] : f1;
 		const int hsel = T1 <= T2[t] ? 0 : (e1[t] > f1 ? 1 : 2);
 		dirb[t] = de3[t] | (df5 << 1) | (hsel << 2);
 	}
-	carryH = H31[NT - 1];
-	carryFp = F31[NT - 1];
+	if (!LAST) carryFp = F31[NT - 1];
 }
 
 /* one group of NT tiles of row i starting at column j0: loads from the row ring, ssw_tb_tiles, stores */
-template <int NT>
+template <int NT, bool LAST, bool PRE = false>
 __device__ static __forceinline__ void ssw_tb_row_group(int i, int j0, int beg, int end, int pbeg, bool top_oob, int lane, int rd,
                                                        const int32_t* Hprev, const int32_t* Eprev, int32_t* Hcur, int32_t* Ecur, int mask,
                                                        const int8_t* smat, int n, const int8_t* ref, uint8_t* drow,
-                                                       int gapO, int gapE, int g, int& carryF, int& carryH, int& carryFp,
-                                                       int& bestv, int& besti, int& bestj)
+                                                       int gapO, int gapE, int g, int& carryF, int& carryFp,
+                                                       int& bestv, int& besti, int& bestj, const int* spre = nullptr)
 {
 	bool act[NT];
 	int j[NT], Hup[NT], Eup[NT], Hdg[NT], s[NT], Hv[NT], Ev[NT], dirb[NT];
@@ -234,10 +256,10 @@ __device__ static __forceinline__ void ssw_tb_row_group(int i, int j0, int beg, 
 				if (!(j[t] == end && top_oob)) { Hup[t] = Hprev[j[t] & mask]; Eup[t] = Eprev[j[t] & mask]; }
 				if (j[t] - 1 >= pbeg) Hdg[t] = Hprev[(j[t] - 1) & mask];
 			}
-			s[t] = (int)smat[(int)ref[j[t]] * n + rd];
+			s[t] = PRE ? spre[t] : (int)smat[(int)ref[j[t]] * n + rd];      /* PRE: looked up ahead of the row (first group) */
 		}
 	}
-	ssw_tb_tiles<NT>(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryH, carryFp, Hv, Ev, dirb,
+	ssw_tb_tiles<NT, LAST>(act, i, j, beg, lane, Hup, Eup, Hdg, s, gapO, gapE, g, carryF, carryFp, Hv, Ev, dirb,
 	                 NT == 1 ? min(32, end - j0 + 1) : 32);
 #pragma unroll
 	for (int t = 0; t < NT; ++t) {
@@ -268,37 +290,58 @@ __device__ static __forceinline__ void ssw_tb_band_fill(int lane, int ql, int rl
 	constexpr unsigned FULL = 0xffffffffu;
 	const int mask = ring - 1;
 	const int W = 2 * bw + 1;
-	int32_t* Hrow[2] = {mine, mine + ring};
-	int32_t* Erow[2] = {mine + 2 * ring, mine + 3 * ring};
 	bestv = 0; besti = 0; bestj = 0;
 	int rd_next = (int)read[0];
+	int letn[4];                                         /* reference letters of the next row's first group (clamped into the reference) */
+#pragma unroll
+	for (int t = 0; t < 4; ++t) letn[t] = (int)ref[min(32 * t + lane, rl - 1)];
 	for (int i = 0; i < ql; ++i) {
-		const int cur = i & 1, prv = cur ^ 1;
+		/* the rows as offsets from the one shared-memory base: LDS/STS (an array of row pointers indexed by the row parity
+		 * lives in local memory and turns every row access into a generic load behind a local load; measured equally fast) */
+		const int cur = (i & 1) * ring, prv = ring - cur;
+		int32_t* const Hc = mine + cur;
+		int32_t* const Ec = mine + 2 * ring + cur;
+		const int32_t* const Hp = mine + prv;
+		const int32_t* const Ep = mine + 2 * ring + prv;
 		const int beg = max(0, i - bw), end = min(rl - 1, i + bw);
 		const int pbeg = max(0, i - 1 - bw);
 		const bool top_oob = (i <= bw + 1) || (end == i + bw);
 		const int rd = rd_next;
 		if (i + 1 < ql) rd_next = (int)read[i + 1];
 		uint8_t* drow = dir + (size_t)W * i - beg;
+		/* scores of the row's first group from the letters fetched during the previous row (the letter fetch and the matrix
+		 * look-up behind it would otherwise head the row's dependent chain), then the letters of the next row's first group */
+		int spre[4];
+#if SSW_TB_PRE
+#pragma unroll
+		for (int t = 0; t < 4; ++t) spre[t] = (int)smat[letn[t] * n + rd];
 		{
-			int carryF = -gapO, carryH = 0, carryFp = 0;
+			const int begn = max(0, i + 1 - bw);
+#pragma unroll
+			for (int t = 0; t < 4; ++t) letn[t] = (int)ref[min(begn + 32 * t + lane, rl - 1)];
+		}
+#endif
+		{
+			int carryF = -gapO, carryFp = 0;
 			int j0 = beg;
+#define SSW_TB_GROUP(NT, LAST, PRE)                                                                                          \
+			ssw_tb_row_group<NT, LAST, PRE>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hp, Ep, Hc, Ec, mask, smat, n, ref, drow,      \
+			                                gapO, gapE, g, carryF, carryFp, bestv, besti, bestj, spre)
+			if (j0 <= end) {                                  /* first group: scores looked up ahead */
+				const int tiles = (end - j0) / 32 + 1;
+				if (tiles > 4) { SSW_TB_GROUP(4, false, SSW_TB_PRE != 0); j0 += 128; }
+				else if (tiles >= 3) { SSW_TB_GROUP(4, true, SSW_TB_PRE != 0); j0 += 128; }
+				else if (tiles == 2) { SSW_TB_GROUP(2, true, SSW_TB_PRE != 0); j0 += 64; }
+				else { SSW_TB_GROUP(1, true, SSW_TB_PRE != 0); j0 += 32; }
+			}
 			while (j0 <= end) {
 				const int tiles = (end - j0) / 32 + 1;
-				if (tiles >= 3) {
-					ssw_tb_row_group<4>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
-					                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
-					j0 += 128;
-				} else if (tiles == 2) {
-					ssw_tb_row_group<2>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
-					                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
-					j0 += 64;
-				} else {
-					ssw_tb_row_group<1>(i, j0, beg, end, pbeg, top_oob, lane, rd, Hrow[prv], Erow[prv], Hrow[cur], Erow[cur], mask, smat, n, ref, drow,
-					                    gapO, gapE, g, carryF, carryH, carryFp, bestv, besti, bestj);
-					j0 += 32;
-				}
+				if (tiles > 4) { SSW_TB_GROUP(4, false, false); j0 += 128; }
+				else if (tiles >= 3) { SSW_TB_GROUP(4, true, false); j0 += 128; }
+				else if (tiles == 2) { SSW_TB_GROUP(2, true, false); j0 += 64; }
+				else { SSW_TB_GROUP(1, true, false); j0 += 32; }
 			}
+#undef SSW_TB_GROUP
 		}
 		__syncwarp();
 	}
@@ -412,6 +455,7 @@ ssw_banded_smem_kernel(SswTbTask* __restrict__ tasks, int n_tasks,
 	const int ti = (int)blockIdx.x * SSW_TB_WARPS + warp;
 	if (ti >= n_tasks) return;
 	SswTbTask T = tasks[ti];
+	T.dbg_t0 = ssw_globaltimer();
 	const int8_t* ref = refs + T.ref_off;
 	const int8_t* read = qcodes + T.read_off;
 	const int rl = T.ref_len, ql = T.read_len;
@@ -620,6 +664,7 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
                              const int8_t* d_q, const int8_t* d_r, const int8_t* d_mat, int n, int gapO, int gapE,
                              SswDevBuf* scratch, float* ms_acc, int64_t* launches,
                              int tb_maxbw /* "tb_maxbw" option: bands above this use the global-memory kernel (tests: 0) */,
+                             bool carve /* "carve" option: largest shared-memory carve-out for the traceback kernels */,
                              int tb_spec /* "tb_spec" option: 0 = band-doubling rounds one after the other, 1 = side by side (speculative kernel),
                                             -1 = side by side when the batch is too small to keep the device busy anyway */,
                              const std::function<int(size_t, const uint32_t*, int32_t, int)>& emit)
@@ -731,10 +776,12 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 					smem = std::max(smem, ints * sizeof(int32_t));
 				}
 				if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(ssw_banded_spec_kernel<0>), smem)) return -1;
+				if (carve && ssw_prefer_max_smem(reinterpret_cast<const void*>(ssw_banded_spec_kernel<0>))) return -1;
 				ssw_launch(ssw_banded_spec_kernel<0>, dim3((unsigned)cnt), dim3(nw * 32), smem, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE, base, d_cig, nw);
 			} else if (ring) {
 				const size_t smem = (size_t)SSW_TB_WARPS * 4 * (size_t)ring * sizeof(int32_t) + (size_t)n * n + 16;
 				if (ssw_ensure_dyn_smem(reinterpret_cast<const void*>(ssw_banded_smem_kernel), smem)) return -1;
+				if (carve && ssw_prefer_max_smem(reinterpret_cast<const void*>(ssw_banded_smem_kernel))) return -1;
 				ssw_launch(ssw_banded_smem_kernel, grid, dim3(SSW_TB_THREADS), smem, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE, base, d_cig, ring);
 			} else {
 				ssw_launch(ssw_banded_kernel, grid, dim3(SSW_TB_THREADS), 0, st, d_tasks + g0, cnt, d_q, d_r, d_mat, n, gapO, gapE,
@@ -780,8 +827,10 @@ static int ssw_traceback_run(cudaStream_t stream, cudaStream_t* side /* 3 side s
 		if (getenv("SSW_TRACE")) {
 			double f = 0, w = 0, s = 0; int nf = 0; long long fmax = 0, wmax = 0;
 			for (const SswTbTask& x : bt) { f += (double)x.dbg_fill; fmax = std::max<long long>(fmax, x.dbg_fill); if (x.dbg_walk) { w += (double)x.dbg_walk; s += (double)x.dbg_score; wmax = std::max<long long>(wmax, x.dbg_walk); ++nf; } }
-			fprintf(stderr, "[libssw-b200 trace] traceback round: %zu tasks in %d launches | fill avg %.0f max %lld clk | %d finished: walk avg %.0f max %lld, rescore avg %.0f clk\n",
-			        bt.size(), n_groups, f / bt.size(), fmax, nf, nf ? w / nf : 0.0, wmax, nf ? s / nf : 0.0);
+			long long t0min = 0x7fffffffffffffffLL, t0max = 0;
+			for (const SswTbTask& x : bt) if (x.dbg_t0) { t0min = std::min<long long>(t0min, x.dbg_t0); t0max = std::max<long long>(t0max, x.dbg_t0); }
+			fprintf(stderr, "[libssw-b200 trace] traceback round: %zu tasks in %d launches | fill avg %.0f max %lld clk | %d finished: walk avg %.0f max %lld, rescore avg %.0f clk | task starts spread over %.2f ms\n",
+			        bt.size(), n_groups, f / bt.size(), fmax, nf, nf ? w / nf : 0.0, wmax, nf ? s / nf : 0.0, t0max > 0 ? (double)(t0max - t0min) * 1e-6 : 0.0);
 		}
 		std::vector<size_t> next;
 		for (size_t i = 0; i < batch.size(); ++i) {

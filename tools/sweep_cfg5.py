@@ -14,14 +14,15 @@ ap.add_argument("sets", nargs="*", default=[""])
 ap.add_argument("--reads", type=int, default=1000)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--flag", type=int, default=2)
+ap.add_argument("--lib", default="libssw.so")
 a = ap.parse_args()
 L = load_package()
 ref, reads = C.make_dna_workload(100_000, a.reads, 10_000, seed_ref=5005, seed_reads=5006, decoy_frac=0.0, p_sub=0.05, p_ins=0.02, p_del=0.02)
 mat = C.dna_matrix(2, 2)
 cells = float(sum(len(q) for q in reads)) * float(len(ref))
-ALL = ("slices", "slice_taper", "slice_prio", "tail_spec", "super", "parts", "tb_spec")
-DEFAULTS = {"slices": 0, "slice_taper": 0, "slice_prio": 0, "tail_spec": 0, "super": 0, "parts": 0, "tb_spec": -1}
-eng = L.BatchAligner(device=0)
+ALL = ("carve", "slices", "slice_taper", "super", "parts", "tb_spec")
+DEFAULTS = {"carve": 1, "slices": 0, "slice_taper": 0, "super": 0, "parts": 0, "tb_spec": -1}
+eng = L.BatchAligner(device=0, lib_name=a.lib)
 eng.set_sequences(reads, [ref])
 eng.align(mat, 5, 3, 1, flag=a.flag, filters=0, filterd=32767, mask_len=5000, score_size=2)      # warm-up (allocations)
 first = None
@@ -42,7 +43,7 @@ for spec in a.sets:
     if first is None:
         first = sig
     b = int(np.argmin(walls))
-    print(json.dumps({"opts": spec or "defaults", "best_ms": round(min(walls), 2), "median_ms": round(float(np.median(walls)), 2),
+    print(json.dumps({"lib": a.lib, "opts": spec or "defaults", "best_ms": round(min(walls), 2), "median_ms": round(float(np.median(walls)), 2),
                       "gcups_best": round(cells / min(walls) / 1e6, 1), "same_results": sig == first,
                       "fwd": round(tms[b]["fill_forward_ms"], 1), "rev": round(tms[b]["fill_reverse_ms"], 1), "tb": round(tms[b]["traceback_ms"], 1)}), flush=True)
 eng.close()
