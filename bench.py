@@ -368,6 +368,12 @@ def sub_result(st, world, name, what, extra=None):
          "phases_ms": {"fill_forward": st["fill_ms"], "resolve": st["resolve_ms"], "fill_reverse": st["reverse_ms"], "traceback": st["traceback_ms"],
                        "note": "max over ranks, per step; phases of slices running on helper streams overlap, so they may add up to more than the step"},
          "alu_roofline": alu_roofline(st["cells"] / world, st["fill_ms"] * 1e-3), "pairs": st["pairs"], "byte_overflows": st["byte_overflows"]}
+    if st["fill_ms"] > st["step_ms"]:
+        # slices on helper streams: their fill times are taken while they share the device and add up to more than the step
+        o["alu_roofline"] = alu_roofline(st["cells"] / world, st["step_ms"] * 1e-3)
+        o["alu_roofline"]["basis"] += ("; denominator = the whole step (forward fills of concurrent slices overlap with reverse fills and tracebacks, "
+                                       "their summed times exceed the step): a lower bound of the fill kernels' own efficiency "
+                                       "(kernel alone: profiles/ncu_strips_cfg5_r2.txt)")
     if extra:
         o.update(extra)
     return o

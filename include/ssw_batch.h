@@ -165,7 +165,11 @@ int ssw_engine_last_timing(const ssw_engine* e, ssw_engine_timing* t);
  *   "latency_cols"  passes over at most this many reference columns use the 32-lane instances (0 = never)
  *   "parts"         CTAs per task of the strip-pipelined kernel: 0 automatic, 1 never split, 2 / 4 forced
  *   "super"         columns per super-block of the strip-pipelined kernel
- *   "slices"        long-read CIGAR batches cut into slices on helper engines: 0 automatic, 1 never, 2 / 3 forced
+ *   "slices"        long-read CIGAR batches cut into slices on helper engines: 0 automatic (three equal slices, from 512
+ *                   pairs on six slices each 80 % of the one before it), 1 never, 2 .. 8 forced
+ *   "slice_taper"   t in 1 .. 99: every slice holds t % of the pairs of the one before it (0 = equal slices / automatic)
+ *   "carve"         1 (default): the kernels of the long-read phases ask for the largest shared-memory carve-out, so that
+ *                   their launches can share SMs; 0: the driver's choice per launch (measurements)
  *   "grid_min"      smallest full score-only grid that is planned on the device
  *   "grid_split"    grids of at least this many pairs are cut into launch groups whose records are copied back while the
  *                   next group computes (default 4 Mi pairs); "grid_group": smallest group in query pairs (default 16)
