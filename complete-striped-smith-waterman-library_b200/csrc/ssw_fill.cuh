@@ -52,12 +52,18 @@
 #define SSW_STRIP_SUPER 4096                /* columns per super-block (granularity of early termination) */
 #define SSW_STRIP_BPAD 32                   /* words in front of every boundary array (scan positions down to -32) */
 
-/* word offset of row k of lane `lane` inside one letter's profile block (32*R words):
- * R = 4a + rem; the first 4a rows are a uint4 segments [seg][lane], the tail is [lane][rem]. */
+/* rows per lane as the profile STORES them: R, or R + 1 when R = 4a + 3 (three tail words per lane cannot be read with one
+ * aligned load; such a lane gets a full fourth segment whose last word is never used: R = 19 is stored like 20 rows and
+ * computed as 19 -- 300 aa protein queries pad to 304 rows in word mode, ssw.c:393, and 16 lanes x 19 rows fit them exactly) */
+template <int R>
+struct SswProfRows { static constexpr int S = (R % 4 == 3) ? R + 1 : R; };
+
+/* word offset of row k of lane `lane` inside one letter's profile block (32*S words):
+ * S = 4a + rem; the first 4a rows are a uint4 segments [seg][lane], the tail is [lane][rem]. */
 template <int R>
 __host__ __device__ static __forceinline__ int ssw_prof_slot(int k, int lane)
 {
-	constexpr int A = R / 4, REM = R % 4;
+	constexpr int S = SswProfRows<R>::S, A = S / 4, REM = S % 4;
 	return k < 4 * A ? (k / 4) * 128 + lane * 4 + (k % 4) : A * 128 + lane * REM + (k - 4 * A);
 }
 
@@ -96,7 +102,7 @@ __device__ static __forceinline__ uint32_t ssw_lds32(ssw_saddr a)
 
 /* shared-memory bytes for an alphabet of n letters */
 template <int R>
-static inline size_t ssw_fill_smem_bytes(int n, int warps = SSW_FILL_WARPS) { return (size_t)warps * (size_t)(n + 1) * 32 * R * sizeof(uint32_t); }   /* profiles only; the snapshot area (ssw_snap_smem_bytes) comes on top */
+static inline size_t ssw_fill_smem_bytes(int n, int warps = SSW_FILL_WARPS) { return (size_t)warps * (size_t)(n + 1) * 32 * SswProfRows<R>::S * sizeof(uint32_t); }   /* profiles only; the snapshot area (ssw_snap_smem_bytes) comes on top */
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* shared device code                                                                                          */
@@ -118,7 +124,7 @@ __device__ static __forceinline__ void ssw_build_profile(uint32_t* prof, int lan
 		cb[k] = row < qb.len ? (int)qcodes[qb.off + (qb.rev ? qb.len - 1 - row : row)] : (row < qb.lp ? -1 : -2);
 	}
 	for (int letter = letter0; letter <= n; letter += letter_step) {
-		uint32_t* pl = prof + letter * (32 * R);
+		uint32_t* pl = prof + letter * (32 * SswProfRows<R>::S);
 #pragma unroll
 		for (int k = 0; k < R; ++k) {
 			int a = SSW_NEG16, b = SSW_NEG16;
@@ -135,16 +141,17 @@ __device__ static __forceinline__ void ssw_build_profile(uint32_t* prof, int lan
 template <int R>
 __device__ static __forceinline__ void ssw_load_scores(uint32_t (&s)[R], ssw_saddr pbase, ssw_saddr ptail, int letter)
 {
-	constexpr int A4 = R / 4, REM = R % 4;
-	const ssw_saddr pl = ssw_sadd(pbase, letter * (32 * R));
+	constexpr int S = SswProfRows<R>::S, A4 = S / 4, REM = S % 4;
+	const ssw_saddr pl = ssw_sadd(pbase, letter * (32 * S));
 #pragma unroll
 	for (int q = 0; q < A4; ++q) {
 		const uint4 v = ssw_lds128(ssw_sadd(pl, q * 128));
-		s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z; s[4 * q + 3] = v.w;
+		s[4 * q] = v.x; s[4 * q + 1] = v.y; s[4 * q + 2] = v.z;
+		if (4 * q + 3 < R) s[4 * q + 3] = v.w;               /* S == R + 1: the last stored word is unused */
 	}
-	if (REM == 1) s[4 * A4] = ssw_lds32(ssw_sadd(ptail, letter * (32 * R)));
+	if (REM == 1) s[4 * A4] = ssw_lds32(ssw_sadd(ptail, letter * (32 * S)));
 	if (REM == 2) {
-		const uint2 v = ssw_lds64(ssw_sadd(ptail, letter * (32 * R)));
+		const uint2 v = ssw_lds64(ssw_sadd(ptail, letter * (32 * S)));
 		s[4 * A4] = v.x; s[4 * A4 + 1] = v.y;
 	}
 }
@@ -351,10 +358,11 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
                 uint32_t* __restrict__ colmax, SswItemBest* __restrict__ bests, int share)
 {
 	static_assert(G == 8 || G == 16 || G == 32, "group width");
-	static_assert(R % 4 != 3 && R >= 1 && R <= 20, "rows per lane");
+	static_assert(R >= 1 && R <= 20, "rows per lane");
 	static_assert(!TERM || G == 32, "early termination is per warp");
 	constexpr int GPW = 32 / G;                 /* groups per warp */
-	constexpr int A4 = R / 4, REM = R % 4;
+	constexpr int S = SswProfRows<R>::S;        /* rows per lane as stored in the profile */
+	constexpr int A4 = S / 4, REM = S % 4;
 	constexpr unsigned FULL = 0xffffffffu;
 
 	SSW_DYN_SMEM(uint32_t, smem);
@@ -362,7 +370,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	const int g = lane / G, t = lane % G;
 	/* share != 0: the host guarantees that all items of this CTA have the same two queries, so one profile serves
 	 * every warp (built cooperatively); otherwise each warp keeps the profile(s) of its own groups */
-	uint32_t* prof = share ? smem : smem + (size_t)warp * (size_t)(n + 1) * 32 * R;
+	uint32_t* prof = share ? smem : smem + (size_t)warp * (size_t)(n + 1) * 32 * S;
 
 	const int nwarps = (int)(blockDim.x >> 5);           /* SSW_FILL_WARPS, fewer when per-warp profiles are large */
 	const int item_idx = ((int)blockIdx.x * nwarps + warp) * GPW + g;
@@ -414,7 +422,7 @@ ssw_fill_kernel(const SswItem* __restrict__ items, int n_items,
 	SswLaneBest lb;
 	lb.best = 0; lb.pos0 = lb.pos1 = -1; lb.row0 = lb.row1 = 0;      /* position -1: no recorded event (yet) */
 	SswSnap<R> snap;
-	ssw_snap_init<R>(snap, reinterpret_cast<uint4*>(smem + (size_t)(share ? 1 : nwarps) * (size_t)(n + 1) * 32 * R), (int)threadIdx.x);
+	ssw_snap_init<R>(snap, reinterpret_cast<uint4*>(smem + (size_t)(share ? 1 : nwarps) * (size_t)(n + 1) * 32 * S), (int)threadIdx.x);
 	uint32_t blk_acc = 0;                               /* CM == 2: running maximum of the current block (last lane) */
 
 	for (int body = 0; body < n_body; ++body) {
