@@ -209,14 +209,15 @@ void write_sam(s_align* a, const Record& ref, const Record& read, const std::str
 void usage()
 {
 	fprintf(stderr, "\nUsage: ssw_batch_cli [options] ... <target.fasta> <query.fasta>(or <query.fastq>)\n"
-	                "Options (as ssw_test): -m N  -x N  -o N  -e N  -p  -a FILE  -c  -f N  -r  -s  -h\n\n");
+	                "Options (as ssw_test): -m N  -x N  -o N  -e N  -p  -a FILE  -c  -f N  -r  -s  -h\n"
+	                "         and -g N: cut the batch over N GPUs (0: all visible ones; default 1)\n\n");
 }
 
 }  // namespace
 
 int main(int argc, char** argv)
 {
-	int match = 2, mismatch = 2, gap_open = 3, gap_ext = 1, filter = 0;
+	int match = 2, mismatch = 2, gap_open = 3, gap_ext = 1, filter = 0, gpus = 1;
 	bool protein = false, path = false, reverse = false, sam = false, header = false;
 	const char* mat_name = nullptr;
 	std::vector<const char*> files;
@@ -231,6 +232,7 @@ int main(int argc, char** argv)
 			case 'e': if (has_val) gap_ext = atoi(argv[++i]); break;
 			case 'f': if (has_val) filter = atoi(argv[++i]); break;
 			case 'a': if (has_val) mat_name = argv[++i]; break;
+			case 'g': if (has_val) gpus = atoi(argv[++i]); break;
 			case 'p': protein = true; break;
 			case 'c': path = true; break;
 			case 'r': reverse = true; break;
@@ -238,7 +240,7 @@ int main(int argc, char** argv)
 			case 'h': header = true; break;
 			default: break;
 			}
-			if (*c == 'm' || *c == 'x' || *c == 'o' || *c == 'e' || *c == 'f' || *c == 'a') break;
+			if (*c == 'm' || *c == 'x' || *c == 'o' || *c == 'e' || *c == 'f' || *c == 'a' || *c == 'g') break;
 		}
 	}
 	if (files.size() < 2) { usage(); return 1; }
@@ -278,15 +280,21 @@ int main(int argc, char** argv)
 	const int32_t n_q = (int32_t)reads.size() * (rc ? 2 : 1), n_r = (int32_t)refs.size();
 	if (n_q == 0 || n_r == 0) return 0;
 
-	ssw_engine* eng = ssw_engine_create(-1);
-	if (!eng) return 1;
+	/* -g N: the batch is cut over N GPUs of this process (0: all visible ones), see ssw_batch.h "Device groups" */
+	ssw_engine* eng = gpus == 1 ? ssw_engine_create(-1) : nullptr;
+	ssw_group* grp = gpus == 1 ? nullptr : ssw_group_create(gpus < 0 ? 0 : gpus, nullptr);
+	if (!eng && !grp) return 1;
 	ssw_batch_params P;
 	memset(&P, 0, sizeof P);
 	P.mat = mat.data(); P.n = n; P.gap_open = (uint8_t)gap_open; P.gap_extend = (uint8_t)gap_ext;
 	P.flag = path ? 2 : 0; P.filters = (uint16_t)filter; P.filterd = 0; P.mask_len = -1; P.score_size = 2;
 	std::vector<s_align*> out((size_t)n_q * n_r, nullptr);
-	if (ssw_align_batch_text(eng, &P, table, rc ? 1 : 0, (int32_t)reads.size(), qtext.data(), qoff.data(), n_r, rtext.data(), roff.data(),
-	                         (int64_t)n_q * n_r, nullptr, nullptr, out.data())) {
+	const int failed = eng
+		? ssw_align_batch_text(eng, &P, table, rc ? 1 : 0, (int32_t)reads.size(), qtext.data(), qoff.data(), n_r, rtext.data(), roff.data(),
+		                       (int64_t)n_q * n_r, nullptr, nullptr, out.data())
+		: ssw_group_align_batch(grp, &P, table, rc ? 1 : 0, (int32_t)reads.size(), qtext.data(), qoff.data(), n_r, rtext.data(), roff.data(),
+		                        (int64_t)n_q * n_r, nullptr, nullptr, out.data(), 0, nullptr);
+	if (failed) {
 		fprintf(stderr, "ssw_align_batch_text failed\n");
 		return 1;
 	}
@@ -318,6 +326,7 @@ int main(int argc, char** argv)
 		}
 	}
 	for (s_align* a : out) if (a) align_destroy(a);
-	ssw_engine_destroy(eng);
+	if (eng) ssw_engine_destroy(eng);
+	if (grp) ssw_group_destroy(grp);
 	return 0;
 }

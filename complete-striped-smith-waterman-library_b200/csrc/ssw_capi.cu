@@ -41,6 +41,8 @@ struct _profile {
 	int8_t score_size;
 };
 
+s_align* ssw_record_from(const ssw_batch_result& r, const uint32_t* pool);
+
 namespace {
 /*
  * The engines behind ssw_align / ssw_align_batch(NULL, ...).  The reference's ssw_align is re-entrant (no locks, no
@@ -102,22 +104,27 @@ struct PoolGuard {
 	~PoolGuard() { if (e) pool_release(e); }
 };
 
-s_align* record_from(const ssw_batch_result& r, const uint32_t* pool)
+inline s_align* record_from(const ssw_batch_result& r, const uint32_t* pool) { return ssw_record_from(r, pool); }
+}  // namespace
+
+/* one batch record as a heap s_align (NULL where ssw_align returns NULL); also used by the device groups (ssw_group.cpp) */
+s_align* ssw_record_from(const ssw_batch_result& r, const uint32_t* pool)
 {
 	if (r.status) return nullptr;
 	s_align* a = (s_align*)calloc(1, sizeof(s_align));
+	if (!a) return nullptr;
 	a->score1 = r.score1; a->score2 = r.score2;
 	a->ref_begin1 = r.ref_begin1; a->ref_end1 = r.ref_end1;
 	a->read_begin1 = r.read_begin1; a->read_end1 = r.read_end1;
 	a->ref_end2 = r.ref_end2; a->flag = r.flag;
 	if (r.cigar_off >= 0 && r.cigar_len > 0) {
 		a->cigar = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)r.cigar_len);   /* libc heap: callers free() it */
+		if (!a->cigar) { free(a); return nullptr; }
 		memcpy(a->cigar, pool + r.cigar_off, sizeof(uint32_t) * (size_t)r.cigar_len);
 		a->cigarLen = r.cigar_len;
 	}
 	return a;
 }
-}  // namespace
 
 /* ssw_engine_set_option(NULL, name, value): every engine of the pool, present and future */
 int ssw_default_engines_option(const char* name, int64_t value)

@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 
 #include "../../include/ssw.h"
 #include "../../include/ssw_batch.h"
@@ -199,8 +201,15 @@ uint16_t Aligner::Align(const char* query, const char* ref, const Filter& filter
 	return Align(query, strlen(query), ref, strlen(ref), filter, alignment, maskLen);
 }
 
+namespace {
+/* device groups of AlignBatch(devices != 1): made on first use, one per device count, shared by all aligners of the
+ * process (a group runs one batch at a time) */
+std::mutex g_group_mu;
+std::map<int32_t, ssw_group*> g_groups;
+}
+
 bool Aligner::AlignBatch(const std::vector<std::string>& queries, const Filter& filter, std::vector<Alignment>& alignments,
-                         std::vector<uint16_t>* flags, int32_t maskLen) const
+                         std::vector<uint16_t>* flags, int32_t maskLen, int32_t devices) const
 {
 	alignments.assign(queries.size(), Alignment());
 	if (flags) flags->assign(queries.size(), 0);
@@ -225,9 +234,18 @@ bool Aligner::AlignBatch(const std::vector<std::string>& queries, const Filter& 
 	std::vector<s_align*> res(origin.size(), nullptr);
 	std::vector<int32_t> nm(origin.size(), 0);
 	/* the '=' / 'X' expansion, the soft clips and the mismatch counts of every path come from the device (ssw_mark.cuh) */
-	if (ssw_align_batch_marked(nullptr, &P, (int32_t)origin.size(), codes.data(), off.data(), 1, ref_codes_.data(), roff,
-	                           (int64_t)origin.size(), nullptr, nullptr, res.data(), nm.data()))
-		return false;
+	if (devices == 1) {
+		if (ssw_align_batch_marked(nullptr, &P, (int32_t)origin.size(), codes.data(), off.data(), 1, ref_codes_.data(), roff,
+		                           (int64_t)origin.size(), nullptr, nullptr, res.data(), nm.data()))
+			return false;
+	} else {
+		std::lock_guard<std::mutex> lock(g_group_mu);
+		ssw_group*& g = g_groups[devices < 0 ? 0 : devices];
+		if (!g) g = ssw_group_create(devices < 0 ? 0 : devices, nullptr);
+		if (!g || ssw_group_align_batch(g, &P, nullptr, 0, (int32_t)origin.size(), codes.data(), off.data(), 1, ref_codes_.data(), roff,
+		                                (int64_t)origin.size(), nullptr, nullptr, res.data(), 1, nm.data()))
+			return false;
+	}
 	for (size_t k = 0; k < origin.size(); ++k) {
 		if (!res[k]) { if (flags) (*flags)[origin[k]] = 1; continue; }
 		if (res[k]->cigarLen > 0) convert_marked(*res[k], nm[k], alignments[origin[k]]);

@@ -361,6 +361,12 @@ extern "C" void ssw_engine_destroy(ssw_engine* e)
 
 extern "C" const char* ssw_engine_device_name(const ssw_engine* e) { return e ? e->dev_name.c_str() : ""; }
 
+extern "C" int32_t ssw_device_count(void)
+{
+	int count = 0;
+	return cudaGetDeviceCount(&count) == cudaSuccess && count > 0 ? count : 0;
+}
+
 extern "C" int ssw_engine_set_option(ssw_engine* e, const char* name, int64_t value)
 {
 	if (!name) return -1;
@@ -1834,7 +1840,7 @@ extern "C" int ssw_engine_align(ssw_engine* e, const ssw_batch_params* params,
                                 uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used)
 {
 	/* nothing may unwind through the C ABI (std::bad_alloc from the planners' vectors, std::length_error, ...) */
-	try { SswBusyGuard busy; return engine_align_impl(e, params, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_cap, pool_used); }
+	try { SswBusyGuard busy(e ? e->device : 0); return engine_align_impl(e, params, n_pairs, pair_query, pair_ref, results, cigar_pool, pool_cap, pool_used); }
 	catch (const std::exception& ex) { fprintf(stderr, "[libssw-b200] ssw_engine_align: %s\n", ex.what()); return -1; }
 	catch (...) { return -1; }
 }

@@ -19,9 +19,15 @@ inline std::atomic<unsigned long long>& ssw_alloc_epoch() { static std::atomic<u
 /* engines currently inside an align call: every planner may claim 1 / (engines + 1) of the free device memory for its
  * scratch, so that several engines working on one device at the same time (helper engines of a sliced batch, concurrent
  * ssw_align callers, user-made engines in several threads) cannot claim the same half twice; idle engines do not count */
-inline std::atomic<int>& ssw_live_engines() { static std::atomic<int> n{0}; return n; }
-struct SswBusyGuard { SswBusyGuard() { ++ssw_live_engines(); } ~SswBusyGuard() { --ssw_live_engines(); } };
-inline size_t ssw_budget_share(size_t bytes) { const int n = ssw_live_engines().load(); return bytes / (size_t)((n < 1 ? 1 : n) + 1); }
+inline std::atomic<int>& ssw_live_engines(int device) { static std::atomic<int> n[64]; return n[device & 63]; }      /* per device: engines of a device group do not share memory */
+struct SswBusyGuard { int dev; explicit SswBusyGuard(int device) : dev(device) { ++ssw_live_engines(dev); } ~SswBusyGuard() { --ssw_live_engines(dev); } };
+inline size_t ssw_budget_share(size_t bytes)
+{
+	int dev = 0;
+	cudaGetDevice(&dev);          /* the engine made its device current on entry */
+	const int n = ssw_live_engines(dev).load();
+	return bytes / (size_t)((n < 1 ? 1 : n) + 1);
+}
 
 /* 64-bit content hash (four interleaved multiply-xor lanes over 8-byte words): the resident-reference cache of ssw_align */
 inline uint64_t ssw_hash_bytes(const void* data, size_t len)

@@ -279,3 +279,118 @@ class BatchAligner(object):
         t = EngineTiming()
         self.lib.ssw_engine_last_timing(self.h, ct.byref(t))
         return {k: getattr(t, k) for k, _ in EngineTiming._fields_}
+
+
+class GroupAligner(object):
+    """ssw_group_* of include/ssw_batch.h: one batch over several GPUs of this process (one engine and one host thread per
+    device; a full grid is cut by queries, an explicit pair list by DP cells).  Results equal BatchAligner's for the same
+    pairs, whatever the number of devices."""
+
+    def __init__(self, n_devices=0, devices=None, lib_dir=None, lib_name=LIB_NAME):
+        self.lib = _load(lib_dir, lib_name)
+        L = self.lib
+        L.ssw_device_count.restype = ct.c_int32
+        L.ssw_group_create.argtypes = [ct.c_int32, ct.POINTER(ct.c_int32)]
+        L.ssw_group_create.restype = ct.c_void_p
+        L.ssw_group_destroy.argtypes = [ct.c_void_p]
+        L.ssw_group_destroy.restype = None
+        L.ssw_group_size.argtypes = [ct.c_void_p]
+        L.ssw_group_size.restype = ct.c_int32
+        L.ssw_group_engine.argtypes = [ct.c_void_p, ct.c_int32]
+        L.ssw_group_engine.restype = ct.c_void_p
+        L.ssw_engine_set_option.argtypes = [ct.c_void_p, ct.c_char_p, ct.c_int64]
+        L.ssw_engine_set_option.restype = ct.c_int
+        L.ssw_engine_last_timing.argtypes = [ct.c_void_p, ct.POINTER(EngineTiming)]
+        L.ssw_engine_last_timing.restype = ct.c_int
+        L.ssw_group_align.argtypes = [ct.c_void_p, ct.POINTER(BatchParams), ct.POINTER(ct.c_int8), ct.c_int32,
+                                      ct.c_int32, ct.c_void_p, ct.POINTER(ct.c_int64), ct.c_int32, ct.c_void_p, ct.POINTER(ct.c_int64),
+                                      ct.c_int64, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), ct.c_void_p, ct.POINTER(ct.c_uint32),
+                                      ct.c_int64, ct.POINTER(ct.c_int64), ct.c_int32, ct.POINTER(ct.c_int32)]
+        L.ssw_group_align.restype = ct.c_int
+        dev = None
+        if devices is not None:
+            dev_a = np.ascontiguousarray(devices, dtype=np.int32)
+            n_devices = len(dev_a)
+            dev = dev_a.ctypes.data_as(ct.POINTER(ct.c_int32))
+        self.h = L.ssw_group_create(int(n_devices), dev)
+        if not self.h:
+            raise RuntimeError("ssw_group_create failed: no usable CUDA device (this library has no CPU path)")
+
+    def close(self):
+        if self.h:
+            self.lib.ssw_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        return int(self.lib.ssw_group_size(self.h))
+
+    def set_option(self, name, value):
+        """The same option on every engine of the group."""
+        for i in range(self.size):
+            if self.lib.ssw_engine_set_option(self.lib.ssw_group_engine(self.h, i), name.encode(), int(value)):
+                raise ValueError(name)
+
+    def timing(self):
+        """Per-device timing records of the last call."""
+        out = []
+        for i in range(self.size):
+            t = EngineTiming()
+            self.lib.ssw_engine_last_timing(self.lib.ssw_group_engine(self.h, i), ct.byref(t))
+            out.append({k: getattr(t, k) for k, _ in EngineTiming._fields_})
+        return out
+
+    def align(self, queries, refs, mat, n, gap_open=3, gap_extend=1, flag=0, filters=0, filterd=0, mask_len=-1, score_size=2,
+              pair_query=None, pair_ref=None, table=None, add_reverse_complement=False, marked=False, n_pairs=None):
+        """Sequences (lists of int8 code arrays, or of bytes / str with `table`) -> (results[RESULT_DTYPE], cigar_pool[uint32])
+        in pair order, plus nm[int32] when marked (CIGARs as mark_mismatch leaves them).  n_pairs: only the first n_pairs
+        pairs of the full grid (no pair lists)."""
+        mat, matp = _i8(mat)
+        P = BatchParams(matp, n, gap_open, gap_extend, flag, filters, filterd, mask_len, score_size)
+        if table is None:
+            qc, qo = concat(queries)
+            rc, ro = concat(refs)
+            qptr, rptr, tabp = qc.ctypes.data_as(ct.c_void_p), rc.ctypes.data_as(ct.c_void_p), None
+        else:
+            qs = [q.encode() if isinstance(q, str) else bytes(q) for q in queries]
+            rs = [r.encode() if isinstance(r, str) else bytes(r) for r in refs]
+            qc = np.frombuffer(b"".join(qs) + b"\0", dtype=np.uint8)
+            rc = np.frombuffer(b"".join(rs) + b"\0", dtype=np.uint8)
+            qo = np.zeros(len(qs) + 1, dtype=np.int64); qo[1:] = np.cumsum([len(q) for q in qs])
+            ro = np.zeros(len(rs) + 1, dtype=np.int64); ro[1:] = np.cumsum([len(r) for r in rs])
+            tab = np.ascontiguousarray(table, dtype=np.int8)
+            assert tab.size == 128
+            qptr, rptr, tabp = qc.ctypes.data_as(ct.c_void_p), rc.ctypes.data_as(ct.c_void_p), tab.ctypes.data_as(ct.POINTER(ct.c_int8))
+        ql, rl = np.diff(qo), np.diff(ro)
+        if table is not None and add_reverse_complement:
+            ql = np.concatenate([ql, ql])
+        if pair_query is None:
+            n_pairs = len(ql) * len(rl) if n_pairs is None else int(n_pairs)
+            pq = pr = None
+            QL, RL = np.repeat(ql, len(rl))[:n_pairs], np.tile(rl, len(ql))[:n_pairs]
+        else:
+            pq_a = np.ascontiguousarray(pair_query, dtype=np.int32)
+            pr_a = np.ascontiguousarray(pair_ref, dtype=np.int32)
+            n_pairs = len(pq_a)
+            pq = pq_a.ctypes.data_as(ct.POINTER(ct.c_int32))
+            pr = pr_a.ctypes.data_as(ct.POINTER(ct.c_int32))
+            QL, RL = ql[np.clip(pq_a, 0, len(ql) - 1)], rl[np.clip(pr_a, 0, len(rl) - 1)]      # the library checks the indices
+        res = np.empty(n_pairs, dtype=RESULT_DTYPE)
+        cap = int(np.sum(QL + np.minimum(RL, QL * 128) + 4)) if (flag & 7) else 0
+        pool = np.empty(max(cap, 1), dtype=np.uint32)
+        used = ct.c_int64(0)
+        nm = np.zeros(n_pairs, dtype=np.int32)
+        rv = self.lib.ssw_group_align(self.h, ct.byref(P), tabp, 1 if add_reverse_complement else 0,
+                                      len(queries), qptr, qo.ctypes.data_as(ct.POINTER(ct.c_int64)),
+                                      len(refs), rptr, ro.ctypes.data_as(ct.POINTER(ct.c_int64)),
+                                      n_pairs, pq, pr, res.ctypes.data_as(ct.c_void_p), pool.ctypes.data_as(ct.POINTER(ct.c_uint32)),
+                                      len(pool), ct.byref(used), 1 if marked else 0, nm.ctypes.data_as(ct.POINTER(ct.c_int32)))
+        if rv:
+            raise RuntimeError("ssw_group_align failed (%d)" % rv)
+        return (res, pool[: used.value], nm) if marked else (res, pool[: used.value])

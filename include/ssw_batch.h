@@ -140,6 +140,51 @@ int ssw_align_batch_text(ssw_engine* e, const ssw_batch_params* params, const in
                          int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
                          s_align** out);
 
+/*
+ * Device groups: one batch over several GPUs of one process (main.c:462-532 is a loop over independent pairs; nothing is
+ * exchanged while the matrices are filled, so the pair list is simply cut).  A group holds one engine per device and
+ * runs every engine from its own host thread.
+ *   full grid (pair lists NULL, n_pairs = all queries x all references): the QUERIES are cut into contiguous blocks of
+ *       nearly equal total length (equal DP cells, as all of them meet the same references); every device receives its
+ *       block of queries and all references and computes its rows of the grid;
+ *   explicit pair list: the LIST is cut into contiguous blocks of nearly equal DP cells (query length x reference length:
+ *       the split of ssw_dist.shard_bounds); pairs that share a reference stay together; sequences are replicated.
+ * Records land in the caller's arrays in pair order exactly as one engine would deliver them; the CIGAR words of the
+ * devices are concatenated (cigar_off re-based).  Results do not depend on the number of devices.
+ */
+typedef struct ssw_group ssw_group;
+
+/* Number of usable CUDA devices (0 if none). */
+int32_t ssw_device_count(void);
+
+/* n_devices <= 0: all visible devices; devices == NULL: devices 0 .. n_devices-1.  NULL on failure. */
+ssw_group* ssw_group_create(int32_t n_devices, const int32_t* devices);
+void ssw_group_destroy(ssw_group* g);
+int32_t ssw_group_size(const ssw_group* g);
+/* The i-th engine of the group (options, timing of its share of the last call); owned by the group. */
+ssw_engine* ssw_group_engine(ssw_group* g, int32_t i);
+
+/*
+ * set_sequences + align over the devices of the group.  `table` == NULL: queries / refs are codes (int8_t, as
+ * ssw_engine_set_sequences takes them); otherwise they are text translated with `table` on the devices, and
+ * add_reverse_complement != 0 adds query n_queries + k = reverse complement of query k (ssw_engine_set_sequences_text).
+ * marked != 0 (needs a CIGAR flag): the CIGARs come back as mark_mismatch would leave them and nm[p] (may be NULL)
+ * receives the mismatch counts (ssw_engine_mark_mismatch); pool_cap is then counted in marked words.
+ */
+int ssw_group_align(ssw_group* g, const ssw_batch_params* params, const int8_t* table, int32_t add_reverse_complement,
+                    int32_t n_queries, const void* queries, const int64_t* query_off,
+                    int32_t n_refs, const void* refs, const int64_t* ref_off,
+                    int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                    ssw_batch_result* results, uint32_t* cigar_pool, int64_t pool_cap, int64_t* pool_used,
+                    int32_t marked, int32_t* nm);
+
+/* The same with heap s_align records (ssw_align_batch / _text / _marked over a group); release with align_destroy. */
+int ssw_group_align_batch(ssw_group* g, const ssw_batch_params* params, const int8_t* table, int32_t add_reverse_complement,
+                          int32_t n_queries, const void* queries, const int64_t* query_off,
+                          int32_t n_refs, const void* refs, const int64_t* ref_off,
+                          int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref,
+                          s_align** out, int32_t marked, int32_t* nm);
+
 /* Device-time breakdown of the last ssw_engine_align call (CUDA events on the engine's stream), in ms. */
 typedef struct {
 	float fill_forward_ms;   /* matrix fill kernels, forward pass (incl. byte->word reruns) */

@@ -68,9 +68,11 @@ public:
 
   /* NEW: all queries against the stored reference in one GPU batch.  alignments[i] is what
    * Align(queries[i], ...) returns; maskLen < 0 uses length/2 of each query (the CLI's choice, main.c:465).
-   * flags (optional) receives the per-query return value of Align.  Returns false if nothing was aligned. */
+   * flags (optional) receives the per-query return value of Align.  Returns false if nothing was aligned.
+   * devices: GPUs of this process the batch is cut over (ssw_batch.h device groups; 1 = the current device,
+   * 0 = all visible devices); the alignments do not depend on it. */
   bool AlignBatch(const std::vector<std::string>& queries, const Filter& filter, std::vector<Alignment>& alignments,
-                  std::vector<uint16_t>* flags = nullptr, int32_t maskLen = 0) const;
+                  std::vector<uint16_t>* flags = nullptr, int32_t maskLen = 0, int32_t devices = 1) const;
 
   /* drop matrices and reference; ReBuild*() make the aligner usable again (the first two only after Clear()) */
   void Clear();

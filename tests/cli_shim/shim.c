@@ -111,3 +111,19 @@ s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t refLen, con
 }
 
 const uint8_t encoded_ops[128] = { ['M'] = 0, ['I'] = 1, ['D'] = 2, ['N'] = 3, ['S'] = 4, ['H'] = 5, ['P'] = 6, ['='] = 7, ['X'] = 8 };
+
+/* device groups (ssw_batch.h): the front ends' -g N / devices != 1 paths; here one "device" answers for all of them */
+struct ssw_group { int n; };
+ssw_group* ssw_group_create(int32_t n_devices, const int32_t* devices) { (void)devices; ssw_group* g = (ssw_group*)calloc(1, sizeof(struct ssw_group)); g->n = n_devices > 0 ? n_devices : 1; return g; }
+void ssw_group_destroy(ssw_group* g) { free(g); }
+int32_t ssw_group_size(const ssw_group* g) { return g ? g->n : 0; }
+int ssw_group_align_batch(ssw_group* g, const ssw_batch_params* P, const int8_t* table, int32_t add_rc,
+                          int32_t n_queries, const void* queries, const int64_t* query_off,
+                          int32_t n_refs, const void* refs, const int64_t* ref_off,
+                          int64_t n_pairs, const int32_t* pair_query, const int32_t* pair_ref, s_align** out, int32_t marked, int32_t* nm)
+{
+	(void)g;
+	if (table) return ssw_align_batch_text(NULL, P, table, add_rc, n_queries, (const char*)queries, query_off, n_refs, (const char*)refs, ref_off, n_pairs, pair_query, pair_ref, out);
+	if (marked) return ssw_align_batch_marked(NULL, P, n_queries, (const int8_t*)queries, query_off, n_refs, (const int8_t*)refs, ref_off, n_pairs, pair_query, pair_ref, out, nm);
+	return ssw_align_batch(NULL, P, n_queries, (const int8_t*)queries, query_off, n_refs, (const int8_t*)refs, ref_off, n_pairs, pair_query, pair_ref, out);
+}

@@ -135,7 +135,11 @@ int main()
 		std::vector<Alignment> res(qs.size());
 		std::vector<uint16_t> rcs(qs.size(), 0);
 #ifdef WITH_BATCH
+#ifdef BATCH_DEVICES          // our wrapper only: the batch cut over that many GPUs (device groups) -- same output
+		const bool ok = b.AlignBatch(qs, f_all, res, &rcs, 25, BATCH_DEVICES);
+#else
 		const bool ok = b.AlignBatch(qs, f_all, res, &rcs, 25);
+#endif
 		if (!ok) printf("AlignBatch failed\n");
 #else
 		for (size_t i = 0; i < qs.size(); ++i) rcs[i] = b.Align(qs[i].c_str(), qs[i].size(), f_all, res[i], 25);

@@ -212,7 +212,8 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 struct cudaDeviceProp { char name[256]; int multiProcessorCount; size_t totalGlobalMem; int major, minor; size_t sharedMemPerBlockOptin; };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+/* SSW_EMU_DEVICES=N: report N identical devices (the host logic of device groups; all of them are this CPU) */
+static inline cudaError_t cudaGetDeviceCount(int* n) { const char* v = getenv("SSW_EMU_DEVICES"); *n = v && atoi(v) > 0 ? atoi(v) : 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {

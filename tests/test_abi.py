@@ -13,7 +13,8 @@ import common as C
 DECLARED = ["ssw_init", "init_destroy", "ssw_align", "align_destroy", "mark_mismatch", "encoded_ops",
             "ssw_engine_create", "ssw_engine_destroy", "ssw_engine_device_name", "ssw_engine_set_sequences",
             "ssw_engine_align", "ssw_align_batch", "ssw_engine_last_timing", "ssw_engine_set_option",
-            "ssw_engine_set_sequences_text", "ssw_align_batch_text", "ssw_engine_mark_mismatch", "ssw_align_batch_marked", "ssw_engine_set_sequences_packed"]
+            "ssw_engine_set_sequences_text", "ssw_align_batch_text", "ssw_engine_mark_mismatch", "ssw_align_batch_marked", "ssw_engine_set_sequences_packed",
+            "ssw_device_count", "ssw_group_create", "ssw_group_destroy", "ssw_group_size", "ssw_group_engine", "ssw_group_align", "ssw_group_align_batch"]
 LEAKED_BY_REFERENCE = ["add_cigar", "store_previous_m"]       # non-static in ssw.c:984,994
 
 
