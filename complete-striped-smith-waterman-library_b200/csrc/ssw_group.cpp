@@ -41,12 +41,16 @@ struct Shard {
 	bool grid = false;
 	int32_t q0 = 0, q1 = 0;          /* grid: block of the caller's queries */
 	int64_t p0 = 0, p1 = 0;          /* list: block of the pair list */
+	ssw_batch_result* ext = nullptr;  /* the caller's records where the block is contiguous in pair order (written in place), else res */
 	std::vector<ssw_batch_result> res;
+	int64_t n = 0;                   /* pairs of this block */
 	std::vector<int32_t> nm;
 	std::unique_ptr<uint32_t[]> pool;
 	int64_t used = 0;
 	int rc = 0;
-	int64_t pairs() const { return (int64_t)res.size(); }
+	int64_t pairs() const { return n; }
+	ssw_batch_result* records() { return ext ? ext : res.data(); }
+	const ssw_batch_result* records() const { return ext ? ext : res.data(); }
 };
 
 /* world+1 boundaries of contiguous blocks of nearly equal total weight (ssw_dist.shard_bounds) */
@@ -87,7 +91,7 @@ void run_shard(ssw_engine* e, const Job& J, Shard& S)
 		const int32_t* pq = nullptr; const int32_t* pr = nullptr;
 		if (S.grid) {
 			nq_loc = S.q1 - S.q0;
-			if (nq_loc <= 0) { S.res.clear(); return; }
+			if (nq_loc <= 0) return;
 			qoff.resize((size_t)nq_loc + 1);
 			for (int32_t k = 0; k <= nq_loc; ++k) qoff[k] = J.qoff[S.q0 + k] - J.qoff[S.q0];
 			const char* qbase = J.q + J.qoff[S.q0];
@@ -108,7 +112,7 @@ void run_shard(ssw_engine* e, const Job& J, Shard& S)
 			}
 		} else {
 			n_pairs = S.p1 - S.p0;
-			if (n_pairs <= 0) { S.res.clear(); return; }
+			if (n_pairs <= 0) return;
 			S.rc = J.table ? ssw_engine_set_sequences_text(e, J.n_q, J.q, J.qoff, J.n_r, J.r, J.roff, J.table, P.n, J.add_rc)
 			               : ssw_engine_set_sequences(e, J.n_q, (const int8_t*)J.q, J.qoff, J.n_r, (const int8_t*)J.r, J.roff);
 			if (S.rc) return;
@@ -117,22 +121,24 @@ void run_shard(ssw_engine* e, const Job& J, Shard& S)
 			pq = J.pq + S.p0; pr = J.pr + S.p0;
 			if (want_cigar) for (int64_t p = 0; p < n_pairs; ++p) cap += cigar_bound(qoff[pq[p] + 1] - qoff[pq[p]], J.roff[pr[p] + 1] - J.roff[pr[p]], P.gap_extend);
 		}
-		S.res.resize((size_t)n_pairs);
+		if (!S.ext) S.res.resize((size_t)n_pairs);
+		S.n = n_pairs;
+		ssw_batch_result* const R = S.records();
 		S.pool.reset(new uint32_t[(size_t)cap + 8]);         /* worst-case sized and mostly untouched: uninitialised storage */
-		S.rc = ssw_engine_align(e, &P, n_pairs, pq, pr, S.res.data(), S.pool.get(), cap + 8, &S.used);
+		S.rc = ssw_engine_align(e, &P, n_pairs, pq, pr, R, S.pool.get(), cap + 8, &S.used);
 		if (S.rc) return;
 		if (J.marked) {
 			S.nm.assign((size_t)n_pairs, 0);
 			if (S.used > 0) {
 				/* a marked CIGAR has at most one word per aligned read base plus the deletions and two clips */
 				int64_t mcap = 0;
-				for (int64_t p = 0; p < n_pairs; ++p) if (S.res[p].cigar_len > 0) {
+				for (int64_t p = 0; p < n_pairs; ++p) if (R[p].cigar_len > 0) {
 					const int32_t q = pq ? pq[p] : (int32_t)(p / J.n_r);
-					mcap += (qoff[q + 1] - qoff[q]) + S.res[p].cigar_len + 2;
+					mcap += (qoff[q + 1] - qoff[q]) + R[p].cigar_len + 2;
 				}
 				std::unique_ptr<uint32_t[]> mpool(new uint32_t[(size_t)mcap + 8]);
 				int64_t mused = 0;
-				S.rc = ssw_engine_mark_mismatch(e, n_pairs, pq, pr, S.res.data(), S.pool.get(), S.used, mpool.get(), mcap + 8, &mused, S.nm.data());
+				S.rc = ssw_engine_mark_mismatch(e, n_pairs, pq, pr, R, S.pool.get(), S.used, mpool.get(), mcap + 8, &mused, S.nm.data());
 				if (S.rc) return;
 				S.pool = std::move(mpool);
 				S.used = mused;
@@ -151,7 +157,7 @@ inline int64_t global_pair(const Job& J, const Shard& S, int64_t l)
 	return l < plus ? (int64_t)S.q0 * J.n_r + l : ((int64_t)J.n_q + S.q0) * J.n_r + (l - plus);
 }
 
-int run_job(ssw_group* g, const Job& J, std::vector<Shard>& shards)
+int run_job(ssw_group* g, const Job& J, std::vector<Shard>& shards, ssw_batch_result* results)
 {
 	const ssw_batch_params& P = *J.P;
 	if (!P.mat || P.n < 1 || P.n > 64) { fprintf(stderr, "[libssw-b200] device group: bad scoring parameters\n"); return -1; }
@@ -175,7 +181,10 @@ int run_job(ssw_group* g, const Job& J, std::vector<Shard>& shards)
 	}
 	if (!JJ.pq) {
 		const std::vector<int64_t> b = balanced_bounds(J.n_q, world, [&](int64_t k) { return J.qoff[k + 1] - J.qoff[k] + 1; });
-		for (int d = 0; d < world; ++d) { shards[d].grid = true; shards[d].q0 = (int32_t)b[d]; shards[d].q1 = (int32_t)b[d + 1]; }
+		for (int d = 0; d < world; ++d) {
+			shards[d].grid = true; shards[d].q0 = (int32_t)b[d]; shards[d].q1 = (int32_t)b[d + 1];
+			if (results && !J.add_rc) shards[d].ext = results + b[d] * J.n_r;         /* rows q0 .. q1 of the grid are contiguous */
+		}
 	} else {
 		for (int64_t p = 0; p < J.n_pairs; ++p)
 			if (JJ.pq[p] < 0 || JJ.pq[p] >= nq_all || JJ.pr[p] < 0 || JJ.pr[p] >= J.n_r) { fprintf(stderr, "[libssw-b200] pair %lld out of range\n", (long long)p); return -1; }
@@ -183,7 +192,7 @@ int run_job(ssw_group* g, const Job& J, std::vector<Shard>& shards)
 			const int32_t q = JJ.pq[p] >= J.n_q ? JJ.pq[p] - J.n_q : JJ.pq[p];
 			return (J.qoff[q + 1] - J.qoff[q] + 1) * (J.roff[JJ.pr[p] + 1] - J.roff[JJ.pr[p]] + 1);
 		});
-		for (int d = 0; d < world; ++d) { shards[d].p0 = b[d]; shards[d].p1 = b[d + 1]; }
+		for (int d = 0; d < world; ++d) { shards[d].p0 = b[d]; shards[d].p1 = b[d + 1]; if (results) shards[d].ext = results + b[d]; }
 	}
 #ifdef SSW_CPU_EMU
 	for (int d = 0; d < world; ++d) run_shard(g->eng[d], JJ, shards[d]);        /* the emulator's fibers are not thread-safe */
@@ -252,21 +261,23 @@ extern "C" int ssw_group_align(ssw_group* g, const ssw_batch_params* params, con
 		if (pool_used) *pool_used = 0;
 		const Job J = make_job(params, table, add_reverse_complement, n_queries, queries, query_off, n_refs, refs, ref_off, n_pairs, pair_query, pair_ref, marked);
 		std::vector<Shard> shards;
-		const int rc = run_job(g, J, shards);
+		const int rc = run_job(g, J, shards, results);
 		if (rc) return rc;
 		int64_t base = 0;
-		for (const Shard& S : shards) {
+		for (Shard& S : shards) {
 			if (S.used > 0) {
 				if (!cigar_pool || base + S.used > pool_cap) { fprintf(stderr, "[libssw-b200] CIGAR pool too small\n"); return -1; }
 				if (base + S.used > 0x7fffffff) { fprintf(stderr, "[libssw-b200] more than 2^31 CIGAR words in one batch: split the batch\n"); return -1; }
 				memcpy(cigar_pool + base, S.pool.get(), sizeof(uint32_t) * (size_t)S.used);
 			}
-			for (int64_t l = 0; l < S.pairs(); ++l) {
-				const int64_t p = global_pair(J, S, l);
-				results[p] = S.res[l];
-				if (results[p].cigar_off >= 0) results[p].cigar_off += (int32_t)base;
-				if (nm) nm[p] = S.nm.empty() ? 0 : S.nm[l];
-			}
+			const bool fix = base > 0 && S.used > 0;
+			if (!S.ext || fix || nm)
+				for (int64_t l = 0; l < S.pairs(); ++l) {
+					const int64_t p = global_pair(J, S, l);
+					if (!S.ext) results[p] = S.res[l];
+					if (fix && results[p].cigar_off >= 0) results[p].cigar_off += (int32_t)base;
+					if (nm) nm[p] = S.nm.empty() ? 0 : S.nm[l];
+				}
 			base += S.used;
 		}
 		if (pool_used) *pool_used = base;
@@ -286,12 +297,12 @@ extern "C" int ssw_group_align_batch(ssw_group* g, const ssw_batch_params* param
 	try {
 		const Job J = make_job(params, table, add_reverse_complement, n_queries, queries, query_off, n_refs, refs, ref_off, n_pairs, pair_query, pair_ref, marked);
 		std::vector<Shard> shards;
-		const int rc = run_job(g, J, shards);
+		const int rc = run_job(g, J, shards, nullptr);
 		if (rc) return rc;
 		for (const Shard& S : shards)
 			for (int64_t l = 0; l < S.pairs(); ++l) {
 				const int64_t p = global_pair(J, S, l);
-				out[p] = ssw_record_from(S.res[l], S.pool.get());
+				out[p] = ssw_record_from(S.records()[l], S.pool.get());
 				if (nm) nm[p] = S.nm.empty() ? 0 : S.nm[l];
 			}
 		return 0;
