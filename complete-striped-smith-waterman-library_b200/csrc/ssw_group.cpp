@@ -199,7 +199,11 @@ int run_job(ssw_group* g, const Job& J, std::vector<Shard>& shards, ssw_batch_re
 #else
 	{
 		std::vector<std::thread> th;
-		for (int d = 1; d < world; ++d) th.emplace_back([&, d] { run_shard(g->eng[d], JJ, shards[d]); });
+		th.reserve((size_t)world);
+		for (int d = 1; d < world; ++d) {
+			try { th.emplace_back([&, d] { run_shard(g->eng[d], JJ, shards[d]); }); }
+			catch (...) { run_shard(g->eng[d], JJ, shards[d]); }       /* no thread to be had: this block runs here */
+		}
 		run_shard(g->eng[0], JJ, shards[0]);
 		for (std::thread& t : th) t.join();
 	}

@@ -12,9 +12,12 @@ from test_emulated_kernels import EMU_DIR, _pkg
 
 n_grids = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-subprocess.run(["make", "-s", "-C", EMU_DIR], check=True, stdout=sys.stderr)
+LIB = os.environ.get("SSW_FUZZ_LIB")        # another build of the emulator library, e.g. one made with -fsanitize=address
+if not LIB:
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True, stdout=sys.stderr)
+    LIB = os.path.join(EMU_DIR, "libssw_emu.so")
 L = _pkg()
-eng = L.BatchAligner(lib_dir=EMU_DIR, lib_name="libssw_emu.so")
+eng = L.BatchAligner(lib_dir=os.path.dirname(LIB), lib_name=os.path.basename(LIB))
 eng.set_option("latency_cols", 0)
 eng.set_option("grid_min", 1)
 rng = np.random.default_rng(seed)
