@@ -264,3 +264,21 @@ int main() {
     one_dev = [l[2:] for l in lines if l.startswith("1 ")]
     three_dev = [l[2:] for l in lines if l.startswith("0 ")]
     assert len(one_dev) == 9 and one_dev == three_dev and sum("s=0 " in l for l in one_dev) == 1
+
+
+def test_c_example_of_the_batch_api(lib, tmp_path):
+    """examples/example_batch.c (plain C99 over include/ssw_batch.h) on the emulator build: the known answer of the reference's
+    example programs (score 21, second best 8 at 4, reference 8..21, read 0..14, two edits, 4=1X4=1I5=), the
+    reverse-complement symmetry of its pairs, and the same output from one and from two devices."""
+    exe = str(tmp_path / "example_batch")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", "-I" + os.path.join(C.ROOT, "include"), "-o", exe,
+                    os.path.join(C.ROOT, "examples", "example_batch.c"), "-L" + EMU_DIR, "-l:libssw_emu.so", "-Wl,-rpath," + EMU_DIR, "-lm"], check=True)
+    env = dict(os.environ, SSW_EMU_DEVICES="2")
+    outs = [subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300, env=env) for n in (1, 2)]
+    assert all(o.returncode == 0 for o in outs), outs[0].stderr[-300:]
+    lines = outs[0].stdout.splitlines()
+    assert outs[0].stdout == outs[1].stdout and len(lines) == 12
+    assert lines[0] == "read 0+ x ref 0: score 21 (second 8 at 4)  ref 8..21  read 0..14  NM 2  4=1X4=1I5="
+    tail = lambda l: l.split(": ", 1)[1]
+    assert tail(lines[6]) == tail(lines[2]) and tail(lines[7]) == tail(lines[3])          # read 0 minus strand == read 1 (its reverse complement)
+    assert subprocess.run([exe, "3"], capture_output=True, env=env).returncode != 0        # more devices than there are
